@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- DAG-loss hot path on B200: DP cells/s, HBM-roofline fraction, CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "C2"): dag_loss forward+backward on a synthetic lattice, B=64 utterances per
+GPU, L=1024 graph vertices, M=256 target tokens, T=L-1 transitions, fp32, ragged lengths off (full lattice).
+One "step" = one dag_loss forward (alpha+beta) + one dag_loss backward (grad_match+grad_links) over the batch,
+inputs resident in HBM.  A DP cell is one (b, t, j) of the padded B x M x L lattice; value = cells/s over all ranks.
+The step's working set (1.27 GB algorithmic) is ~10x the 126 MB L2, so no explicit L2 flush is needed.
+
+Prints ONE JSON line (rank 0).  Extra objects: roofline (dominant kernel, HBM bound, measured peak from
+MEASURED_PEAKS.json), cpu_baseline (CPU oracle = C port of the reference arithmetic, all host threads, bounded
+sample), e2e (same metric through the public operator API with pinned HOST buffers, H2D/D2H inside the timed
+region), clocks (NVML samples during the timed region), parts (other kernels of the path, informational).
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "dag_loss_fwd_bwd_dp_cells_per_sec"
+UNIT = "cells/s"
+C2 = dict(B=64, L=1024, M=256, V=4096)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=C2["B"], help="utterances per GPU")
+    ap.add_argument("--prelen", type=int, default=C2["L"])
+    ap.add_argument("--tarlen", type=int, default=C2["M"])
+    ap.add_argument("--translen", type=int, default=0, help="0 = L-1")
+    ap.add_argument("--vocab", type=int, default=C2["V"])
+    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parts", action="store_true", help="skip the informational per-kernel parts")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(B, M, L, T):
+    N, E = B * M * L, B * L * T
+    return {"fwd": 4 * (3 * N + E), "bwd": 4 * (4 * N + 2 * E), "fwd_bwd": 4 * (7 * N + 3 * E),
+            "viterbi": 4 * (N + E) + 4 * B * L}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """NVML samples of SM clock + throttle reasons while the timed region runs."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in {**self.BAD, **self.NOTE}.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_inputs(torch, dev, B, L, M, T, V, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    match = torch.log(torch.rand(B, M, L, device=dev, generator=g) * 0.98 + 0.01)
+    raw = torch.randn(B, L, T, device=dev, generator=g)
+    i = torch.arange(L, device=dev).view(1, L, 1)
+    k = torch.arange(T, device=dev).view(1, 1, T)
+    valid = (i + k + 1) < L
+    links = torch.log_softmax(raw.masked_fill(~valid, float("-inf")), -1).masked_fill(~valid, float("-inf"))
+    del raw
+    olen = torch.full((B,), L, dtype=torch.long, device=dev)
+    tlen = torch.full((B,), M, dtype=torch.long, device=dev)
+    go = torch.full((B,), 1.0, device=dev)
+    return match.contiguous(), links.contiguous(), olen, tlen, go
+
+
+def cpu_baseline(args, T, with_torch_path=True):
+    """C port of the reference arithmetic (oracle/dag_oracle.c, OpenMP over all host threads) on the first
+    `cpu_sample` utterances of the same workload; optionally also the torch restatement of torch_dag_loss."""
+    import numpy as np
+    from oracle import oracle
+    Bs = max(1, min(args.cpu_sample, args.batch))
+    L, M = args.prelen, args.tarlen
+    match, links, olen, tlen = oracle.make_lattice(Bs, L, M, T, seed=1234, ragged=False)
+    go = np.ones(Bs, np.float32)
+    oracle.dag_loss(match[:1], links[:1], olen[:1], tlen[:1], True, np.float32)  # warm (page in, omp pool)
+    t0 = time.perf_counter()
+    _, a, b = oracle.dag_loss(match, links, olen, tlen, True, np.float32)
+    oracle.dag_loss_backward(go, a, b, match, links, olen, tlen, np.float32)
+    dt = time.perf_counter() - t0
+    out = {"value": Bs * M * L / dt, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+           "sample": "first %d utterances of the workload (B=%d,L=%d,M=%d,T=%d), fp32 fwd+bwd, %.2f s; "
+                     "C/OpenMP restatement of the reference arithmetic (oracle/dag_oracle.c)" % (Bs, Bs, L, M, T, dt),
+           "seconds": dt, "host_cpus": os.cpu_count()}
+    if with_torch_path:
+        try:
+            import torch
+            ops = importlib.import_module("daspeech_b200.custom_ops.dag_loss")
+            m = torch.tensor(match[:1], requires_grad=True)
+            lk = torch.tensor(links[:1])
+            dense = torch.tensor(oracle.dense_links(links[:1])).requires_grad_()
+            t0 = time.perf_counter()
+            loss = ops.torch_dag_loss(m, dense, torch.tensor(olen[:1]), torch.tensor(tlen[:1]))
+            torch.autograd.grad(loss.sum(), [m, dense])
+            dt2 = time.perf_counter() - t0
+            out["torch_path"] = {"value": M * L / dt2, "unit": UNIT, "threads": torch.get_num_threads(),
+                                 "sample": "1 utterance, dense-links torch restatement of torch_dag_loss + autograd "
+                                           "(the reference's CPU algorithm, dag_loss.py:325-366), %.2f s" % dt2}
+            del lk
+        except Exception as e:  # pragma: no cover
+            out["torch_path"] = {"error": str(e)[:200]}
+    return out
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU arm.  The reference's CPU implementation of this path is Python/torch that lives
+    in /root/reference and cannot travel to the GPU box; what runs here is its C/OpenMP port (the oracle)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import oracle
+    L, M = args.prelen, args.tarlen
+    T = args.translen or (L - 1)
+    Bs = max(1, min(args.cpu_sample, args.batch))
+    match, links, olen, tlen = oracle.make_lattice(Bs, L, M, T, seed=1234, ragged=False)
+    go = np.ones(Bs, np.float32)
+
+    def step():
+        _, a, b = oracle.dag_loss(match, links, olen, tlen, True, np.float32)
+        oracle.dag_loss_backward(go, a, b, match, links, olen, tlen, np.float32)
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = Bs * M * L / dt
+    sample = ("each step = first %d utterances of the workload, fp32 fwd+bwd, %d timed steps (capped at 5), "
+              "C/OpenMP port of the reference arithmetic" % (Bs, steps))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, T),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, T):
+    return {"workload": "C2 dag_loss fwd+bwd: B=%d utterances/GPU, L=%d vertices, M=%d targets, T=%d transitions, "
+                        "full lengths, fp32" % (args.batch, args.prelen, args.tarlen, T),
+            "global_batch": args.batch * args.gpus, "prelen": args.prelen, "tarlen": args.tarlen, "translen": T,
+            "vocab": args.vocab, "parallelism": "dp%d (utterance-sharded, no data-path collective)" % args.gpus,
+            "l2": "inputs larger than L2 (1.27 GB touched per step vs 126 MB L2); no flush"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: plain `python bench.py --gpus N` re-executes itself under torchrun (one rank per GPU)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   "--nproc-per-node=%d" % args.gpus, "--master-addr", "127.0.0.1",
+                                   "--master-port", os.environ.get("MASTER_PORT", "29541"),
+                                   os.path.abspath(__file__)] + sys.argv[1:])
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    ops = importlib.import_module("daspeech_b200.custom_ops.dag_loss")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, L, M, V = args.batch, args.prelen, args.tarlen, args.vocab
+    T = args.translen or (L - 1)
+    K, W = args.steps, max(args.warmup, 3)
+    k = ops.get_dag_kernel()
+    match, links, olen, tlen, go = make_inputs(torch, dev, B, L, M, T, V, 1234 + rank)
+    bytes_ = algorithmic_bytes(B, M, L, T)
+    peak_gbs, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
+        gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+        return alpha, beta, gm, gl
+
+    for _ in range(W):
+        out = step()
+    barrier()
+    # ---- timed region: exactly K steps -------------------------------------------------------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    bwd_ev = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with ClockSampler(local) as clk:
+        ev[0].record()
+        for s in range(K):
+            fwd_ev[s][0].record()
+            alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
+            fwd_ev[s][1].record()
+            gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+            bwd_ev[s].record()
+        ev[1].record()
+        barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[1])
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / K
+    cells = B * M * L * world
+    value = cells / (ms_per_step * 1e-3)
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / K
+    bwd_ms = sum(fwd_ev[s][1].elapsed_time(bwd_ev[s]) for s in range(K)) / K
+    loss_check = float(out[1][:, 0, 0].float().mean().item())
+
+    # dominant kernel: forward = ONE launch (dag_alpha_beta_kernel, alpha and beta chains side by side)
+    if fwd_ms >= bwd_ms:
+        dom = {"kernel": "dag_alpha_beta_kernel<float,1024> (dag_loss forward: alpha+beta, one launch)",
+               "ms": fwd_ms, "bytes": bytes_["fwd"]}
+    else:
+        dom = {"kernel": "dag_loss_backward (grad_match_kernel_v4 + grad_links_kernel, two launches timed together)",
+               "ms": bwd_ms, "bytes": bytes_["bwd"]}
+    ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
+                "traffic": None, "kernel": dom["kernel"], "kernel_ms": dom["ms"],
+                "algorithmic_bytes_per_launch": dom["bytes"], "peak_source": peak_src,
+                "step": {"algorithmic_bytes": bytes_["fwd_bwd"], "ms": ms_per_step,
+                         "achieved": bytes_["fwd_bwd"] / (ms_per_step * 1e-3) / 1e9,
+                         "frac": bytes_["fwd_bwd"] / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
+                         "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                         "note": "at T=L-1 the recurrences are exp/issue bound, not HBM bound (DESIGN.md)"}}
+
+    # ---- e2e: public autograd API, pinned host inputs, H2D + D2H inside the timed region -------------
+    h_match = match.cpu().pin_memory()
+    h_links = links.cpu().pin_memory()
+    h_olen, h_tlen = olen.cpu().pin_memory(), tlen.cpu().pin_memory()
+    h_loss = torch.empty(B, dtype=torch.float32).pin_memory()
+    h2d = h_match.numel() * 4 + h_links.numel() * 4 + 16 * B
+    d2h = 4 * B
+
+    def e2e_step():
+        m = h_match.to(dev, non_blocking=True).requires_grad_()
+        lk = h_links.to(dev, non_blocking=True).requires_grad_()
+        ol = h_olen.to(dev, non_blocking=True)
+        tl = h_tlen.to(dev, non_blocking=True)
+        loss = ops.dag_loss(m, lk, ol, tl)
+        total = -(loss / tl).mean()
+        total.backward()
+        h_loss.copy_(loss.detach(), non_blocking=True)
+        return m.grad, lk.grad
+
+    del out, alpha, beta, gm, gl
+    e2e_k = max(3, min(K, 10))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_k):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_k
+    e2e = {"value": cells / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms, "steps": e2e_k,
+           "api": "daspeech_b200.dag_loss(match_all, links, output_length, target_length) + .backward(), "
+                  "inputs from pinned host memory, per-utterance loss read back"}
+
+    # ---- informational parts: the other kernels of the path (rank 0 only) ---------------------------
+    parts = {}
+    if rank == 0 and not args.no_parts:
+        def timeit(fn, n=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b2.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b2) / n
+
+        vit_ms = timeit(lambda: k.dag_best_alignment(match, links, olen, tlen, 1, want_alpha=False))
+        parts["dag_best_alignment"] = {"ms": vit_ms, "algorithmic_bytes": bytes_["viterbi"],
+                                       "gbs": bytes_["viterbi"] / vit_ms / 1e6}
+        for name, dt, esz in (("fp16", torch.float16, 2), ("fp32", torch.float32, 4)):
+            logits = (torch.randn(B, L, V, device=dev) * 2).to(dt)
+            idx = torch.randint(4, V, (B, M), device=dev).unsqueeze(1).expand(-1, L, -1)
+            gsel = torch.randn(B, M, L, device=dev).transpose(1, 2)
+            ms_f = timeit(lambda: k.logsoftmax_gather(logits, idx, True))
+            by_f = 2 * esz * B * L * V + 4 * B * L * M + 8 * B * M
+            ms_b = timeit(lambda: k.logsoftmax_gather_backward(logits, idx, gsel))
+            by_b = 2 * esz * B * L * V + 4 * B * L * M
+            parts["logsoftmax_gather_" + name] = {"fwd_ms": ms_f, "fwd_gbs": by_f / ms_f / 1e6,
+                                                  "fwd_frac": by_f / ms_f / 1e6 / peak_gbs,
+                                                  "bwd_ms": ms_b, "bwd_gbs": by_b / ms_b / 1e6,
+                                                  "bwd_frac": by_b / ms_b / 1e6 / peak_gbs}
+            del logits, idx, gsel
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args, T),
+                "utt_per_sec": B * world / (ms_per_step * 1e-3), "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": 3 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args, T)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,62 @@
+"""ctypes loader for libdagb200.so (the C-ABI declared in include/dagb200.h).
+
+There is NO fallback: if the shared library is missing or a call fails the caller gets a RuntimeError.
+Build it with `python -c "import __graft_entry__ as g; g.build()"` or `python daspeech_b200/csrc/build.py`.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdagb200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/dagb200.h declares
+SIGNATURES = {
+    "dagb200_version": (_int, []),
+    "dagb200_last_error": (ctypes.c_char_p, []),
+    "dagb200_logsoftmax_gather": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
+                                         _int, _int, _int, _int, _int, _vp]),
+    "dagb200_logsoftmax_gather_backward": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
+                                                  _int, _int, _int, _int, _vp]),
+    "dagb200_dag_loss": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),
+    "dagb200_dag_loss_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
+                                         _int, _int, _int, _int, _int, _int, _vp]),
+    "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "dagb200_dag_best_alignment": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int,
+                                          _vp, _sz, _vp, _vp]),
+}
+
+
+def load():
+    """dlopen libdagb200.so and bind every entry point.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "daspeech_b200: %s is missing -- the CUDA extension has not been built and there is no "
+                "CPU/torch fallback. Run `python daspeech_b200/csrc/build.py`." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dagb200_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))

@@ -1,0 +1,116 @@
+/*
+ * dagb200.h -- C ABI of libdagb200.so: B200 (sm_100a) kernels for the DAG-loss hot path of
+ * ictnlp/DASpeech (DASpeech/custom_ops).
+ *
+ * This is the drop-in boundary.  The reference exposes the path through a pybind11 module
+ * `dag_loss_fn` with four functions taking torch::Tensor (DASpeech/custom_ops/dag_loss.cpp:19-29);
+ * each entry point below replaces one of them with plain device pointers, sizes and a CUDA stream
+ * (no torch types).  The Python host layer (daspeech_b200/custom_ops/dag_loss.py) re-creates the
+ * reference's operator surface (dag_loss.py:66-299) on top of these calls via ctypes; INTEGRATION.md
+ * shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; tensors are row-major contiguous
+ *     unless a stride argument is given (strides are in ELEMENTS);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is enqueued
+ *     asynchronously on it, nothing synchronises the host;
+ *   - return value: 0 on success, <0 argument error (DAGB200_E*), >0 a cudaError_t; a human readable
+ *     message for the calling thread's last failure is returned by dagb200_last_error();
+ *   - lengths are int64 (as in the reference, dag_loss.cu:332);
+ *   - `status` (nullable, int32[B]) receives per-sample device-side precondition violations that the
+ *     reference turns into CUDA_KERNEL_ASSERT (dag_loss.cu:68-69, dag_best_alignment.cu:67-70,118):
+ *     0 ok, DAGB200_ST_* otherwise.  Offending samples get -inf alpha/beta (loss -inf) and an all -1
+ *     path instead of a sticky device assert.
+ */
+#ifndef DAGB200_H
+#define DAGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAGB200_VERSION 100
+
+/* element types */
+#define DAGB200_F32 0
+#define DAGB200_F16 1
+#define DAGB200_BF16 2 /* extension: the reference rejects bf16 (logsoftmax_gather.cu:46-58) */
+#define DAGB200_F64 3
+
+/* argument errors */
+#define DAGB200_EINVAL (-1)   /* bad shape / null pointer / bad config */
+#define DAGB200_EDTYPE (-2)   /* unsupported element type */
+#define DAGB200_ELIMIT (-3)   /* size beyond what the kernels index */
+#define DAGB200_EWORKSPACE (-4)
+
+/* per-sample device status */
+#define DAGB200_ST_OK 0
+#define DAGB200_ST_LEN_LT2 1      /* target/output length < 2            (dag_loss.cu:68)   */
+#define DAGB200_ST_GRAPH_SMALL 2  /* output_length < target_length       (dag_loss.cu:69)   */
+#define DAGB200_ST_TOO_SHORT 3    /* (Tn-1)*T+1 < O                      (dag_best_alignment.cu:69) */
+#define DAGB200_ST_NO_PATH 4      /* Viterbi end cell unreachable        (dag_best_alignment.cu:118) */
+
+int dagb200_version(void);
+const char *dagb200_last_error(void);
+
+/* Replaces `logsoftmax_gather` (dag_loss.cpp:22, logsoftmax_gather.cu:313-377).
+ *   logits  [B][L][V] contiguous, dtype F32/F16/BF16/F64; OVERWRITTEN with softmax probabilities
+ *           iff require_gradient != 0 (the reference's in-place contract, dag_loss.py:272-274)
+ *   idx     int64, addressed idx[b*isb + l*isl + s*iss]; the stride-0 expanded view the criterion
+ *           passes (nat_dag_loss.py:127: targets.unsqueeze(1).expand(-1, L, -1)) is isl = 0
+ *   out     float32 (float64 for F64 logits), addressed out[b*osb + l*osl + s*oss]; the host layer
+ *           passes a [B][S][L]-contiguous buffer (osb=S*L, osl=1, oss=L) and returns it as a
+ *           [B,L,S]-shaped view so the criterion's transpose(1,2).contiguous() costs nothing.   */
+int dagb200_logsoftmax_gather(void *logits, int dtype,
+                              const int64_t *idx, int64_t isb, int64_t isl, int64_t iss,
+                              void *out, int64_t osb, int64_t osl, int64_t oss,
+                              int B, int L, int V, int S, int require_gradient, void *stream);
+
+/* Replaces the torch ops of DagLogsoftmaxGatherFunc.backward (dag_loss.py:293-295):
+ *   grad_in = probs * (-sum_s gout[s]);  grad_in[idx[s]] += gout[s]
+ * `probs_inout` [B][L][V] holds the saved probabilities and receives grad_in (same buffer, as the
+ * reference).  gout is float32 (float64 for F64) addressed gout[b*gsb + l*gsl + s*gss].         */
+int dagb200_logsoftmax_gather_backward(void *probs_inout, int dtype,
+                                       const int64_t *idx, int64_t isb, int64_t isl, int64_t iss,
+                                       const void *gout, int64_t gsb, int64_t gsl, int64_t gss,
+                                       int B, int L, int V, int S, void *stream);
+
+/* Replaces `dag_loss` (dag_loss.cpp:19, dag_loss.cu:313-375).
+ *   match [B][M][L], links [B][L][T] (links[b][i][k] = log P(i -> i+k+1)), dtype F32 or F64
+ *   alpha, beta [B][M][L] outputs, fully written (-inf outside the computed wedge); beta is
+ *   computed only when require_gradient != 0 (else filled with -inf, as the reference returns)
+ *   config: 1..4 accepted for signature compatibility (reference tile selector), ignored.        */
+int dagb200_dag_loss(const void *match, const void *links,
+                     const int64_t *output_length, const int64_t *target_length,
+                     void *alpha, void *beta, int dtype,
+                     int B, int M, int L, int T, int require_gradient, int config,
+                     int32_t *status, void *stream);
+
+/* Replaces `dag_loss_backward` (dag_loss.cpp:20, dag_loss.cu:518-571).
+ *   grad_output [B]; grad_match [B][M][L] and grad_links [B][L][T] are fully written.            */
+int dagb200_dag_loss_backward(const void *grad_output, const void *alpha, const void *beta,
+                              const void *match, const void *links,
+                              const int64_t *output_length, const int64_t *target_length,
+                              void *grad_match, void *grad_links, int dtype,
+                              int B, int M, int L, int T, int config1, int config2, void *stream);
+
+/* Replaces `dag_best_alignment` (dag_loss.cpp:21, dag_best_alignment.cu:209-253).
+ *   alpha [B][M][L] (max-plus scores) may be NULL when the caller discards it (the reference's
+ *   Python wrapper does, dag_loss.py:227-230); path int32 [B][L], -1 = vertex not on the path.
+ *   config 1..4 reproduces the reference's tie-break for TRANS_BLOCK_SIZE 4/8/16/32.
+ *   workspace: dagb200_best_alignment_workspace_bytes(B,M,L,T) bytes of device scratch.          */
+size_t dagb200_best_alignment_workspace_bytes(int B, int M, int L, int T);
+int dagb200_dag_best_alignment(const void *match, const void *links,
+                               const int64_t *output_length, const int64_t *target_length,
+                               void *alpha, int32_t *path, int dtype,
+                               int B, int M, int L, int T, int config,
+                               void *workspace, size_t workspace_bytes,
+                               int32_t *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAGB200_H */

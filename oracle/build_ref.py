@@ -35,7 +35,7 @@ def build(verbose=False):
          extra_cuda_cflags=["-DOF_SOFTMAX_USE_FAST_MATH", "-O3"],
          build_directory=OUT, verbose=verbose, is_python_module=False)
     # keep only the shared object (drop ninja files / objects that embed source paths)
-    for f in glob.glob(os.path.join(OUT, "*")):
+    for f in (os.path.join(OUT, n) for n in os.listdir(OUT)):
         if not f.endswith(".so"):
             try:
                 os.remove(f)
