@@ -26,7 +26,9 @@ SIGNATURES = {
                                          _int, _int, _int, _int, _int, _vp]),
     "dagb200_logsoftmax_gather_backward": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                                   _int, _int, _int, _int, _vp]),
-    "dagb200_dag_loss": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp]),
+    "dagb200_dag_loss_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "dagb200_dag_loss": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int,
+                                _vp, _sz, _vp, _vp]),
     "dagb200_dag_loss_backward": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
                                          _int, _int, _int, _int, _int, _int, _vp]),
     "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),

@@ -363,9 +363,24 @@ static int check_dp_args(const char *who, const void *match, const void *links, 
 
 using namespace dagb200;
 
+namespace dagb200 {
+size_t dp2_workspace_bytes(int B, int L);
+bool dp2_supported(int M, int L);
+int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
+                              float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
+                              int32_t *status, cudaStream_t st);
+}  // namespace dagb200
+
+extern "C" size_t dagb200_dag_loss_workspace_bytes(int B, int M, int L, int T) {
+  (void)T;
+  if (B <= 0 || M < 1 || L < 1 || !dp2_supported(M, L)) return 0;
+  return dp2_workspace_bytes(B, L);
+}
+
 extern "C" int dagb200_dag_loss(const void *match, const void *links, const int64_t *output_length,
                                 const int64_t *target_length, void *alpha, void *beta, int dtype, int B, int M,
-                                int L, int T, int require_gradient, int config, int32_t *status, void *stream) {
+                                int L, int T, int require_gradient, int config, void *workspace,
+                                size_t workspace_bytes, int32_t *status, void *stream) {
   int rc = check_dp_args("dag_loss", match, links, output_length, target_length, dtype, B, M, L, T);
   if (rc) return rc;
   DAGB200_CHECK_ARG(config >= 1 && config <= 4, DAGB200_EINVAL, "config should be 1~4");
@@ -379,6 +394,9 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
     cudaError_t e = cudaMemsetAsync(beta, 0, (size_t)B * M * L * esz, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(beta)");
   }
+  if (dtype == DAGB200_F32 && workspace && dp2_supported(M, L) && workspace_bytes >= dp2_workspace_bytes(B, L))
+    return launch_alpha_beta_blocked((const float *)match, (const float *)links, output_length, target_length,
+                                     (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
   if (dtype == DAGB200_F32)
     return launch_alpha_beta<float>((const float *)match, (const float *)links, output_length, target_length,
                                     (float *)alpha, (float *)beta, B, M, L, T, grad, status, st);

@@ -1,0 +1,55 @@
+// dag_tiles.cuh -- layout of the per-call transition-probability scratch shared by the precompute kernel
+// (dag_prep.cu) and the blocked recurrences (dag_dp2.cu).
+//
+// Vertices are grouped in blocks of 32.  For every utterance the scratch holds, for NB = ceil(L/32):
+//   rmax  [NB*32]            per-source-vertex max_k links[i][k] over valid successors (-inf if none)
+//   diagA [NB][32][32] fp32  P'[32J+ii][32J+jj]            (row ii, lane jj)   -- alpha chain, strictly upper
+//   diagB [NB][32][32] fp32  P'[32J+jj][32J+nn] at [nn][jj] (row nn, lane jj)  -- beta chain
+//   tilesA[NB(NB-1)/2] 4 KB  off-diagonal tile (I<J) as the B operand of mma.m16n8k16 with K = source vertex,
+//                            N = destination vertex, bf16 hi plane then bf16 lo plane, in FRAGMENT order
+//   tilesB[NB(NB-1)/2] 4 KB  the same tile as the B operand with K = destination vertex, N = source vertex
+// with P'[i][j] = exp(links[i][j-i-1] - rmax[i])  (0 outside the band / beyond the graph).
+//
+// Fragment order of one 32(K) x 32(N) operand tile Bop[k][n]: eight uint4 "units" q, unit q is stored as 32
+// consecutive uint4 (one per lane -> a warp load of a unit is one fully coalesced 512-byte access).
+//   q < 4: hi plane, q >= 4: lo plane;  qq = q & 3;  ks = qq >> 1 (k16 step);  nt0 = 2 * (qq & 1)
+//   .x = reg(nt0, 0)  .y = reg(nt0, 1)  .z = reg(nt0+1, 0)  .w = reg(nt0+1, 1)
+//   reg(nt, r) = { Bop[16ks + 2tig + 8r][8nt + gid] (low half), Bop[16ks + 2tig + 8r + 1][8nt + gid] (high half) }
+//   gid = lane >> 2, tig = lane & 3   -- exactly the b0/b1 registers of mma.sync.m16n8k16.row.col
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+namespace dagb200 {
+
+constexpr int kBlk = 32;            // vertices per block
+constexpr int kTileBytes = 4096;    // one off-diagonal operand tile (hi + lo planes)
+
+struct TileLayout {
+  int NB;                // blocks per utterance
+  size_t off_rmax, off_diagA, off_diagB, off_tilesA, off_tilesB, sample_bytes;
+  __host__ __device__ static inline TileLayout make(int L) {
+    TileLayout t;
+    t.NB = (L + kBlk - 1) / kBlk;
+    const size_t ntri = (size_t)t.NB * (t.NB - 1) / 2;
+    size_t o = 0;
+    t.off_rmax = o;   o += (size_t)t.NB * kBlk * sizeof(float);
+    t.off_diagA = o;  o += (size_t)t.NB * kBlk * kBlk * sizeof(float);
+    t.off_diagB = o;  o += (size_t)t.NB * kBlk * kBlk * sizeof(float);
+    t.off_tilesA = o; o += ntri * kTileBytes;
+    t.off_tilesB = o; o += ntri * kTileBytes;
+    t.sample_bytes = (o + 255) & ~(size_t)255;
+    return t;
+  }
+  // tile (I < J) for the alpha direction: the J-1... panel of destination block J is contiguous in I
+  __host__ __device__ inline size_t idxA(int I, int J) const { return (size_t)J * (J - 1) / 2 + I; }
+  // tile (Jb < Nb) for the beta direction: the panel of source block Jb is contiguous in Nb
+  __host__ __device__ inline size_t idxB(int Jb, int Nb) const {
+    return (size_t)Jb * (2 * NB - Jb - 1) / 2 + (Nb - Jb - 1);
+  }
+};
+
+// number of 32-blocks a band of T transitions reaches beyond the adjacent block
+__host__ __device__ inline int band_blocks(int T) { return 1 + (T - 1) / kBlk; }
+
+}  // namespace dagb200

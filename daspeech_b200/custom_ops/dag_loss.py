@@ -33,6 +33,10 @@ _DEBUG = os.environ.get("DAGB200_DEBUG", "0") not in ("", "0")
 # .contiguous() (dag_loss.py:103) -- with this layout both are free.  Set to False for a plain contiguous result.
 TRANSPOSED_GATHER_OUTPUT = True
 
+# False (default): fp32 lattices run the blocked tensor-core recurrences (flush-to-zero contract in DESIGN.md).
+# True: always run the exact log-domain kernels (bit-for-bit the reference's -inf structure, ~100x slower at C2).
+EXACT_LOG_DOMAIN = os.environ.get("DAGB200_EXACT", "0") not in ("", "0")
+
 _STATUS_TEXT = {
     1: "dag_best_alignment: target/output length should at least 2",
     2: "dag_best_alignment: graph size is too small (smaller than target length)",
@@ -103,11 +107,15 @@ class _DagKernel:
         alpha = torch.empty((bsz, tarlen, prelen), dtype=match_all.dtype, device=match_all.device)
         beta = torch.empty_like(alpha)
         status = torch.empty(bsz, dtype=torch.int32, device=match_all.device) if _DEBUG else None
+        nbytes = 0
+        if EXACT_LOG_DOMAIN is False and match_all.dtype == torch.float32:
+            nbytes = int(self.lib.dagb200_dag_loss_workspace_bytes(bsz, tarlen, prelen, translen))
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=match_all.device) if nbytes else None
         with torch.cuda.device(match_all.device):
             rc = self.lib.dagb200_dag_loss(_ptr(match_all), _ptr(links), _ptr(output_length), _ptr(target_length),
                                            _ptr(alpha), _ptr(beta), _DTYPE_CODE[match_all.dtype],
                                            bsz, tarlen, prelen, translen, int(bool(require_gradient)), int(config),
-                                           _ptr(status), _stream())
+                                           _ptr(workspace), nbytes, _ptr(status), _stream())
         _lib.check(rc, "dag_loss")
         _check_status(status)
         return alpha, beta

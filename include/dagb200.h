@@ -81,12 +81,17 @@ int dagb200_logsoftmax_gather_backward(void *probs_inout, int dtype,
 /* Replaces `dag_loss` (dag_loss.cpp:19, dag_loss.cu:313-375).
  *   match [B][M][L], links [B][L][T] (links[b][i][k] = log P(i -> i+k+1)), dtype F32 or F64
  *   alpha, beta [B][M][L] outputs, fully written (-inf outside the computed wedge); beta is
- *   computed only when require_gradient != 0 (else filled with -inf, as the reference returns)
- *   config: 1..4 accepted for signature compatibility (reference tile selector), ignored.        */
+ *   computed only when require_gradient != 0 (else zero-filled, exactly what the reference returns)
+ *   config: 1..4 accepted for signature compatibility (reference tile selector), ignored.
+ *   workspace: device scratch of dagb200_dag_loss_workspace_bytes(B,M,L,T) bytes.  With it (fp32 only) the
+ *   blocked tensor-core recurrences run; with workspace == NULL (or fp64, or a lattice beyond their
+ *   shared-memory limits) the exact log-domain kernels run.                                        */
+size_t dagb200_dag_loss_workspace_bytes(int B, int M, int L, int T);
 int dagb200_dag_loss(const void *match, const void *links,
                      const int64_t *output_length, const int64_t *target_length,
                      void *alpha, void *beta, int dtype,
                      int B, int M, int L, int T, int require_gradient, int config,
+                     void *workspace, size_t workspace_bytes,
                      int32_t *status, void *stream);
 
 /* Replaces `dag_loss_backward` (dag_loss.cpp:20, dag_loss.cu:518-571).

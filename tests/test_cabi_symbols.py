@@ -43,13 +43,13 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_argument_errors_are_reported_without_touching_the_gpu(lib):
     # bad config (reference: TORCH_CHECK "config should be 1~4", dag_loss.cu:351)
-    rc = lib.dagb200_dag_loss(1, 1, 1, 1, 1, 1, 0, 2, 4, 8, 7, 1, 9, None, None)
+    rc = lib.dagb200_dag_loss(1, 1, 1, 1, 1, 1, 0, 2, 4, 8, 7, 1, 9, None, 0, None, None)
     assert rc == -1 and b"config should be 1~4" in lib.dagb200_last_error()
     # unsupported lattice dtype (reference dispatch covers float/double only)
-    rc = lib.dagb200_dag_loss(1, 1, 1, 1, 1, 1, 1, 2, 4, 8, 7, 1, 1, None, None)
+    rc = lib.dagb200_dag_loss(1, 1, 1, 1, 1, 1, 1, 2, 4, 8, 7, 1, 1, None, 0, None, None)
     assert rc == -2 and b"float32 or float64" in lib.dagb200_last_error()
     # null pointers
-    rc = lib.dagb200_dag_loss(None, None, None, None, None, None, 0, 2, 4, 8, 7, 1, 1, None, None)
+    rc = lib.dagb200_dag_loss(None, None, None, None, None, None, 0, 2, 4, 8, 7, 1, 1, None, 0, None, None)
     assert rc == -1
     rc = lib.dagb200_dag_loss_backward(1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 2, 4, 8, 7, 3, 1, None)
     assert rc == -1 and b"config1" in lib.dagb200_last_error()
@@ -59,7 +59,8 @@ def test_argument_errors_are_reported_without_touching_the_gpu(lib):
     assert rc == -2
     assert lib.dagb200_best_alignment_workspace_bytes(2, 4, 8, 7) == 2 * 4 * 8 * 2
     # empty batch is a no-op
-    assert lib.dagb200_dag_loss(None, None, None, None, None, None, 0, 0, 4, 8, 7, 1, 1, None, None) == 0
+    assert lib.dagb200_dag_loss(None, None, None, None, None, None, 0, 0, 4, 8, 7, 1, 1, None, 0, None, None) == 0
+    assert lib.dagb200_dag_loss_workspace_bytes(64, 256, 1024, 1023) > 64 * 4 * 1024 * 1024
 
 
 def test_missing_library_fails_loudly(monkeypatch):
