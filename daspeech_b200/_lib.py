@@ -22,6 +22,8 @@ _sz = ctypes.c_size_t
 SIGNATURES = {
     "dagb200_version": (_int, []),
     "dagb200_last_error": (ctypes.c_char_p, []),
+    "dagb200_set_exact": (None, [_int]),
+    "dagb200_get_exact": (_int, []),
     "dagb200_logsoftmax_gather": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                          _int, _int, _int, _int, _int, _vp]),
     "dagb200_logsoftmax_gather_backward": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,

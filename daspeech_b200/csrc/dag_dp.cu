@@ -366,6 +366,7 @@ using namespace dagb200;
 namespace dagb200 {
 size_t dp2_workspace_bytes(int B, int L);
 bool dp2_supported(int M, int L);
+extern int g_exact_mode;
 int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
                               int32_t *status, cudaStream_t st);
@@ -394,7 +395,7 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
     cudaError_t e = cudaMemsetAsync(beta, 0, (size_t)B * M * L * esz, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(beta)");
   }
-  if (dtype == DAGB200_F32 && workspace && dp2_supported(M, L) && workspace_bytes >= dp2_workspace_bytes(B, L))
+  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp2_supported(M, L) && workspace_bytes >= dp2_workspace_bytes(B, L))
     return launch_alpha_beta_blocked((const float *)match, (const float *)links, output_length, target_length,
                                      (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
   if (dtype == DAGB200_F32)

@@ -1,23 +1,32 @@
 // dag_dp2.cu -- blocked forward (alpha) / backward (beta) recurrences of the DAG loss for sm_100a.
 //
 // Replaces calculate_alpha_kernel / calculate_beta_kernel (reference dag_loss.cu:40-140, 178-274) on the fp32
-// path.  Same recurrence, reorganised so that the transition plane is touched M/R times instead of M times and
-// the predecessor sum of all "far" vertices runs on the tensor cores:
+// path.  Same recurrence, reorganised so that the transition plane is touched M/32 times instead of M times,
+// the predecessor sum of all "far" vertices runs on the tensor cores, and the serial depth of a tile is its 32
+// COLUMNS instead of its rows:
 //
-//   vertices in blocks of 32 (index q in sweep order), target rows in chunks of R steps; tile = (block, chunk)
-//   far part   X[t, j in J] = sum_{i in earlier blocks} exp(a[t-1,i] - f[t,J]) * P'[i,j]
-//              bf16 hi/lo split of both operands (3 mma.sync.m16n8k16 per product -> ~2^-16 relative error),
-//              fp32 accumulation; f[t,J] = max of the far predecessors' log-values, so every operand is <= 1
-//   near part  the 32x32 diagonal block: a 32-lane serial chain per tile, fp32, own frame g = max of the block's
-//              previous row; the two parts are combined in the log domain:
-//              a[t,j] = match[t,j] + L + log(X e^{f-L} + S e^{g-L}),  L = max(f, g)
+//   vertices in blocks of 32 (index q in sweep order), target rows in chunks of 32 steps; tile = (block, chunk)
+//   far part   X[t, j in J] = sum_{i in earlier blocks} exp2(a2[t-1,i] - FI[t,J]) * P'[i,j]
+//              a2 = log2 of the predecessor's outgoing mass, FI = integer upper bound of the far predecessors'
+//              a2 (every operand <= 1, the scaling an exact power of two); both operands are split into bf16
+//              hi/lo (3 mma.sync.m16n8k16 per product, ~2^-16 relative error), fp32 accumulation
+//   near part  the 32x32 diagonal block.  Cell (t, j) only depends on cells with smaller t AND smaller j, so a
+//              warp maps LANES TO ROWS and sweeps the 32 columns serially: at column j every lane r forms the
+//              in-block predecessor sum of its own row for the NEXT row (FMAs on registers), hands it to lane
+//              r+1 with one shuffle, and combines what it received with its far sum and emission.  All values
+//              are block floating point -- a mantissa per cell, an integer exponent per (row, 8-column group),
+//              all lane-private: no cross-lane reduction and nothing transcendental on the dependency path.
 //   schedule   tile (q, c) depends on (q' < q, c) and (q, c-1): anti-diagonal waves inside ONE CTA per
 //              (utterance, direction), __syncthreads between the GEMM phase and the chain phase of a wave.
 //              No inter-CTA communication (the reference spin-waits between CTAs on a global queue).
 //
-// Flush-to-zero contract (DESIGN.md "Numerics"): a far predecessor whose log-value is > 87 nats below the best far
-// predecessor of the same 32-vertex block, or an in-block predecessor > 87 nats below the block's best, contributes
-// exactly 0 (the log-domain reference would carry it at < e^-87 relative weight).
+// Flush-to-zero contract (DESIGN.md "Numerics"): a predecessor contributes exactly 0 when its mass is more than
+// 2^-126 below (far part) the largest far predecessor of the 32-vertex destination block / (near part) the largest
+// in-block predecessor group of the cell; a transition when it is > 87 nats below the best transition of its
+// source vertex; an emission when it is > 87 nats below the best emission of its (row, 8-column group).
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dag_tiles.cuh"
 
@@ -25,6 +34,15 @@ namespace dagb200 {
 
 constexpr int kDp2Threads = 512;
 constexpr int kDp2Warps = kDp2Threads / 32;
+constexpr int kRows = 32;                       // target rows per chunk (= lanes of a chain warp)
+constexpr int kWpt = kRows / 16;                // warps per tile in the GEMM phase
+constexpr int kTpw = kDp2Warps / kWpt;          // tiles per batch
+constexpr int kPitch = 33;                      // padded row pitch of 32x32 fp32 tiles in shared memory
+constexpr int kNegBig = -(1 << 20);             // "empty" integer frame
+constexpr float kLn2Hi = 0.693359375f;          // 355/512, 9 significant bits: k * kLn2Hi is exact for |k| < 2^15
+constexpr float kLn2Lo = -2.12194440e-4f;       // ln2 - kLn2Hi
+
+__device__ long long g_dp2_dbg[8];
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -33,13 +51,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// order-preserving float <-> int map so that the warp maximum is ONE redux.sync
-__device__ __forceinline__ int f2ord(float x) {
-  int i = __float_as_int(x);
-  return i ^ ((i >> 31) & 0x7fffffff);
-}
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-__device__ __forceinline__ float warp_max_redux(float x) { return ord2f(__reduce_max_sync(0xffffffffu, f2ord(x))); }
+// 2^d for integer d <= 127 (0 below the normal range)
+__device__ __forceinline__ float pow2i(int d) { return d < -126 ? 0.f : __int_as_float((d + 127) << 23); }
+// unbiased exponent of a positive normal float
+__device__ __forceinline__ int fexp(float v) { return (int)((__float_as_uint(v) >> 23) & 0xff) - 127; }
 
 __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
@@ -49,35 +64,152 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi, u
   lo = *reinterpret_cast<uint32_t *>(&l);
 }
 
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct Dp2Smem {
-  float *xbuf;   // [TPW][R][32]   far sums of the tiles of the current batch
-  float *fbuf;   // [TPW][R]       their frames
-  float *rmtab;  // [M][NB]        per (row, block q) maximum of the (shifted) log-values
-  float *abuf;   // [warps][32]    chain broadcast buffer
-  float *rmax;   // [NB*32]        per-source-vertex transition maximum
+  float *xbuf;   // [kTpw][32][kPitch] far sums of the tiles of the current batch
+  int *fbuf;     // [kTpw][32]         their integer frames
+  float *ut;     // [kTpw][32][32]     diagonal-block weights of the tiles of the current batch ([cj][ci])
+  float *io;     // [kTpw][32][kPitch] emissions in, lattice values out
+  int *rmtab;    // [M][NB]            per (row, block q) integer upper bound of log2(outgoing mass)
+  float *rmax;   // [NB*32]            per-source-vertex transition maximum
+  float *stm;    // [NB][32]           chain state carried between chunks: mantissas of the chunk's last row
+  int *stf;      // [NB][4]            ... and their group exponents (sweep order)
 };
 
-// One direction of one utterance.  R = rows per chunk (multiple of 16).
-template <bool BETA, int R>
+// ---------------------------------------------------------------------------------------------------------
+// One column of the diagonal-block sweep.  CJ is a compile-time constant so that mant[] stays in registers.
+template <bool BETA, int CJ>
+__device__ __forceinline__ void chain_column(float (&mant)[kBlk], int (&gexp)[4], int &maxe, const float *utw,
+                                             float *iow, const float *xbw, int lane, int FI, float d0m, int d0f,
+                                             const float (&ew)[8], const float (&mm)[8], int KE, bool rowvalid,
+                                             int jbase, int t, int O, const float *rmax_blk) {
+  constexpr int G = CJ >> 3;
+  // (1) predecessor sum of MY row for the next row's column CJ: sum_{ci < CJ} mant[ci] * U[ci][CJ]
+  float dm = 0.f;
+  int df = kNegBig;
+  if (CJ > 0) {
+    float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c4 = 0; c4 < CJ; c4 += 4) {
+      const float4 u4 = *reinterpret_cast<const float4 *>(utw + CJ * kBlk + c4);  // broadcast
+      float s = ps[c4 >> 3];
+      s = fmaf(mant[c4], u4.x, s);
+      if (c4 + 1 < CJ) s = fmaf(mant[c4 + 1], u4.y, s);
+      if (c4 + 2 < CJ) s = fmaf(mant[c4 + 2], u4.z, s);
+      if (c4 + 3 < CJ) s = fmaf(mant[c4 + 3], u4.w, s);
+      ps[c4 >> 3] = s;
+    }
+    constexpr int GL = (CJ > 0 ? CJ - 1 : 0) >> 3;  // last group that has a column < CJ
+#pragma unroll
+    for (int g = 0; g <= GL; g++) df = max(df, gexp[g]);
+#pragma unroll
+    for (int g = 0; g <= GL; g++) dm = fmaf(ps[g], pow2i(gexp[g] - df), dm);
+  }
+  // (2) hand it to the next row; row 0 of the chunk takes the sum formed from the previous chunk's last row
+  float rm = __shfl_up_sync(0xffffffffu, dm, 1);
+  int rf = __shfl_up_sync(0xffffffffu, df, 1);
+  const float zm = __shfl_sync(0xffffffffu, d0m, CJ);
+  const int zf = __shfl_sync(0xffffffffu, d0f, CJ);
+  if (lane == 0) { rm = zm; rf = zf; }
+  // (3) combine with the far sum (frame FI) -> total incoming mass of cell (row, CJ), frame Lm
+  const int jj = BETA ? (kBlk - 1 - CJ) : CJ;
+  const float X = xbw[jj];
+  const int Lm = max(FI, rf);
+  const float tot = fmaf(X, pow2i(FI - Lm), rm * pow2i(rf - Lm));
+  // (4) lattice value (off the dependency path)
+  const int j = jbase + jj;
+  const bool valid = rowvalid && j >= t && j < O;
+  float out = neg_inf_f();
+  if (valid && tot > 0.f) {
+    const float fl = (float)Lm;
+    out = (mm[CJ & 7] + fmaf(__log2f(tot), 0.6931471805599453f, fl * kLn2Lo)) + fl * kLn2Hi;
+    if (BETA) out += rmax_blk[jj];
+  }
+  iow[jj] = out;
+  // (5) outgoing mass of the cell = tot * emission * best transition, stored as mantissa in the group frame
+  const float v = tot * ew[CJ & 7];  // frame Lm + KE ; ew = 0 for invalid cells
+  float mnew = 0.f;
+  if (v > 0.f) {
+    const int fr = Lm + KE;
+    const int e = fexp(v);
+    maxe = max(maxe, fr + e + 1);
+    const float vn = v * pow2i(-e);  // normalised to [1, 2)
+    if (gexp[G] == kNegBig) {
+      gexp[G] = fr + e;
+      mnew = vn;
+    } else {
+      const int shift = fr + e - gexp[G];
+      if (shift > 100) {  // the group frame is far too low for this value: re-frame the group (rare)
+#pragma unroll
+        for (int c = G * 8; c < CJ; c++) mant[c] *= pow2i(-shift);
+        gexp[G] += shift;
+        mnew = vn;
+      } else {
+        mnew = vn * pow2i(shift);
+      }
+    }
+  }
+  mant[CJ] = mnew;
+}
+
+template <bool BETA, int CJ0>
+__device__ __forceinline__ void chain_group(float (&mant)[kBlk], int (&gexp)[4], int &maxe, const float *utw, float *iow,
+                                            const float *xbw, int lane, int FI, float d0m, int d0f, bool rowvalid,
+                                            int jbase, int t, int O, const float *rmax_blk) {
+  // emissions of this row for the 8 columns of the group: scaled exponentials and their integer frame
+  float mm[8], ew[8], w2[8];
+  float wmax = neg_inf_f();
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int cj = CJ0 + k;
+    const int jj = BETA ? (kBlk - 1 - cj) : cj;
+    const int j = jbase + jj;
+    const bool valid = rowvalid && j >= t && j < O;
+    mm[k] = iow[jj];
+    w2[k] = valid ? (mm[k] + rmax_blk[jj]) * kLog2e : neg_inf_f();
+    wmax = fmaxf(wmax, w2[k]);
+  }
+  const int KE = wmax > -1.0e30f ? (int)ceilf(wmax) : kNegBig;
+#pragma unroll
+  for (int k = 0; k < 8; k++) ew[k] = (KE > kNegBig) ? exp2f(w2[k] - (float)KE) : 0.f;
+  chain_column<BETA, CJ0 + 0>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 1>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 2>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 3>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 4>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 5>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 6>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+  chain_column<BETA, CJ0 + 7>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+}
+
+// One direction of one utterance.
+template <bool BETA>
 __device__ void blocked_chain(const float *__restrict__ match, float *__restrict__ lat, const unsigned char *__restrict__ ws,
-                              const TileLayout &lay, const Dp2Smem &sm, int O, int Tn, int M, int L, int Tl) {
-  constexpr int WPT = R / 16;             // warps per tile in the GEMM phase
-  constexpr int TPW = kDp2Warps / WPT;    // tiles per batch
+                              const TileLayout &lay, const Dp2Smem &sm, int O, int Tn, int M, int L, int Tl, bool dbg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const float ninf = neg_inf_f();
   const int NB = lay.NB;
   const int NBv = (O + kBlk - 1) / kBlk;
   const int nsteps = Tn - 1;
-  const int NCv = (nsteps + R - 1) / R;
+  const int NCv = (nsteps + kRows - 1) / kRows;
   const int band = band_blocks(Tl);
   const float *g_rmax = reinterpret_cast<const float *>(ws + lay.off_rmax);
   const float *diag = reinterpret_cast<const float *>(ws + (BETA ? lay.off_diagB : lay.off_diagA));
   const uint4 *tiles = reinterpret_cast<const uint4 *>(ws + (BETA ? lay.off_tilesB : lay.off_tilesA));
 
-  // ---- prologue: -inf padding, the seed row, per-vertex maxima, row-maximum table ------------------------
-  for (int x = threadIdx.x; x < NB * kBlk; x += kDp2Threads) sm.rmax[x] = (x < O) ? g_rmax[x] : ninf;
-  for (int x = threadIdx.x; x < M * NB; x += kDp2Threads) sm.rmtab[x] = ninf;
+  // ---- prologue: -inf padding, the seed row, per-vertex maxima, frame table, chain state ------------------
+  for (int x = threadIdx.x; x < NB * kBlk; x += kDp2Threads) {
+    sm.rmax[x] = (x < O) ? g_rmax[x] : ninf;
+    sm.stm[x] = 0.f;
+  }
+  for (int x = threadIdx.x; x < NB * 4; x += kDp2Threads) sm.stf[x] = kNegBig;
+  for (int x = threadIdx.x; x < M * NB; x += kDp2Threads) sm.rmtab[x] = kNegBig;
   {
     // rows >= Tn entirely, and columns beyond the last valid block of rows < Tn
     const int64_t tail0 = (int64_t)Tn * L;
@@ -93,12 +225,20 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    // seed: outgoing mass of the single start cell, as mantissa * 2^F (sweep-order column index ci)
     const int seed_row = BETA ? Tn - 1 : 0, seed_col = BETA ? O - 1 : 0;
-    const int Jb = seed_col / kBlk;
+    const int Jb = seed_col / kBlk, jj = seed_col % kBlk;
+    const int ci = BETA ? kBlk - 1 - jj : jj;
     const int q = BETA ? NBv - 1 - Jb : Jb;
     float v = match[(int64_t)seed_row * L + seed_col];
     if (!BETA) v += sm.rmax[seed_col];
-    sm.rmtab[seed_row * NB + q] = v;
+    const float v2 = v * kLog2e;
+    if (v2 > -1.0e30f) {
+      const int F = (int)ceilf(v2);
+      sm.stm[q * kBlk + ci] = exp2f(v2 - (float)F);  // in (0.5, 1]
+      sm.stf[q * 4 + (ci >> 3)] = F;
+      sm.rmtab[seed_row * NB + q] = F + 1;
+    }
   }
   __syncthreads();
 
@@ -106,41 +246,62 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
   const int nwaves = NBv + NCv - 1;
   for (int w = 0; w < nwaves; w++) {
     const int c_lo = max(0, w - NBv + 1), c_hi = min(NCv - 1, w);
-    for (int cb = c_lo; cb <= c_hi; cb += TPW) {
+    for (int cb = c_lo; cb <= c_hi; cb += kTpw) {
+      long long tdbg0 = dbg ? clock64() : 0;
       // ================= GEMM phase: far predecessors through the tensor cores =================
       {
-        const int ts = warp / WPT, sl = warp % WPT;
+        const int ts = warp / kWpt, sl = warp % kWpt;
         const int c = cb + ts;
         if (c <= c_hi) {
           const int q = w - c;
           const int J = BETA ? NBv - 1 - q : q;
           const int r0 = 16 * sl + gid, r1 = r0 + 8;
-          const int s0 = c * R + r0, s1 = c * R + r1;
+          const int s0 = c * kRows + r0, s1 = c * kRows + r1;
           const bool v0 = s0 < nsteps, v1 = s1 < nsteps;
           const int tp0 = BETA ? Tn - 1 - s0 : s0, tp1 = BETA ? Tn - 1 - s1 : s1;   // previous-row index
+          // stage this tile's diagonal-block weights and emissions for the chain phase: asynchronous
+          // global->shared copies issued now, landed by the end of the MMA loop (2 warps x 16 rows)
+          {
+            const float *d = diag + (size_t)J * kBlk * kBlk;
+            float *utw = sm.ut + (size_t)ts * kBlk * kBlk;
+            float *iow = sm.io + (size_t)ts * kRows * kPitch;
+            const int j = kBlk * J + lane;
+            for (int rr = sl; rr < kBlk; rr += kWpt) {
+              cp_async_f32(utw + rr * kBlk + lane, d + rr * kBlk + lane);
+              const int s = c * kRows + rr;
+              const int t = BETA ? Tn - 2 - s : 1 + s;
+              if (s < nsteps && j < L) cp_async_f32(iow + rr * kPitch + lane, match + (int64_t)t * L + j);
+              else iow[rr * kPitch + lane] = ninf;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
           const int qlo = max(0, q - band);
-          float f0 = ninf, f1 = ninf;
-          if (v0) for (int qq = qlo; qq < q; qq++) f0 = fmaxf(f0, sm.rmtab[tp0 * NB + qq]);
-          if (v1) for (int qq = qlo; qq < q; qq++) f1 = fmaxf(f1, sm.rmtab[tp1 * NB + qq]);
+          int F0 = kNegBig, F1 = kNegBig;
+          if (v0) for (int qq = qlo; qq < q; qq++) F0 = max(F0, sm.rmtab[tp0 * NB + qq]);
+          if (v1) for (int qq = qlo; qq < q; qq++) F1 = max(F1, sm.rmtab[tp1 * NB + qq]);
           float acc[4][4];
 #pragma unroll
           for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[a][e] = 0.f;
-          // any row of this 16-row slice with a finite far frame?
-          const bool live = __any_sync(0xffffffffu, (v0 && f0 > ninf) || (v1 && f1 > ninf));
+          const bool live = __any_sync(0xffffffffu, F0 > kNegBig || F1 > kNegBig);
           if (live) {
-            const float fs0 = (f0 > ninf) ? f0 * kLog2e : 0.f, fs1 = (f1 > ninf) ? f1 * kLog2e : 0.f;
+            const float fs0 = (F0 > kNegBig) ? (float)F0 : 0.f, fs1 = (F1 > kNegBig) ? (float)F1 : 0.f;
             const float *row0 = lat + (int64_t)(v0 ? tp0 : 0) * L, *row1 = lat + (int64_t)(v1 ? tp1 : 0) * L;
             for (int qq = qlo; qq < q; qq++) {
               const int Js = BETA ? NBv - 1 - qq : qq;
-              // skip source blocks whose previous-row maxima are all -inf for this slice
-              const float m0 = v0 ? sm.rmtab[tp0 * NB + qq] : ninf, m1 = v1 ? sm.rmtab[tp1 * NB + qq] : ninf;
-              if (!__any_sync(0xffffffffu, m0 > ninf || m1 > ninf)) continue;
+              // skip source blocks that are empty on every previous row of this 16-row slice
+              const int m0 = v0 ? sm.rmtab[tp0 * NB + qq] : kNegBig, m1 = v1 ? sm.rmtab[tp1 * NB + qq] : kNegBig;
+              if (!__any_sync(0xffffffffu, m0 > kNegBig || m1 > kNegBig)) continue;
               const uint4 *tp = tiles + (BETA ? lay.idxB(J, Js) : lay.idxA(Js, J)) * (kTileBytes / 16);
               uint4 u[8];
 #pragma unroll
               for (int k8 = 0; k8 < 8; k8++) u[k8] = __ldg(tp + k8 * 32 + lane);
+              if (qq + 2 < q) {  // pull the tile after next towards L2 while this one is being consumed
+                const int Jn = BETA ? NBv - 1 - (qq + 2) : qq + 2;
+                const uint4 *tn = tiles + (BETA ? lay.idxB(J, Jn) : lay.idxA(Jn, J)) * (kTileBytes / 16);
+                prefetch_l2(tn + lane * 8);
+              }
 #pragma unroll
               for (int ks = 0; ks < 2; ks++) {
                 const int col = kBlk * Js + 16 * ks + 2 * tig;
@@ -175,105 +336,104 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
               }
             }
           }
-          float *xb = sm.xbuf + (size_t)ts * R * kBlk;
+          float *xb = sm.xbuf + (size_t)ts * kRows * kPitch;
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) {
-            *reinterpret_cast<float2 *>(xb + r0 * kBlk + 8 * nt + 2 * tig) = make_float2(acc[nt][0], acc[nt][1]);
-            *reinterpret_cast<float2 *>(xb + r1 * kBlk + 8 * nt + 2 * tig) = make_float2(acc[nt][2], acc[nt][3]);
+            const int n = 8 * nt + 2 * tig;
+            xb[r0 * kPitch + n] = acc[nt][0]; xb[r0 * kPitch + n + 1] = acc[nt][1];
+            xb[r1 * kPitch + n] = acc[nt][2]; xb[r1 * kPitch + n + 1] = acc[nt][3];
           }
-          if (tig == 0) { sm.fbuf[ts * R + r0] = f0; sm.fbuf[ts * R + r1] = f1; }
+          if (tig == 0) { sm.fbuf[ts * kRows + r0] = F0; sm.fbuf[ts * kRows + r1] = F1; }
+          asm volatile("cp.async.wait_all;" ::: "memory");
         }
       }
       __syncthreads();
-      // ================= chain phase: the 32x32 diagonal block, one warp per tile =================
+      long long tdbg1 = dbg ? clock64() : 0;
+      // ================= chain phase: the 32x32 diagonal block, one warp per tile, lanes = rows ============
       {
-        const int ts = warp / WPT;
+        const int ts = warp / kWpt;
         const int c = cb + ts;
-        const int cw = (WPT >= 4) ? (ts % WPT) : (WPT == 2 ? ((ts >> 1) & 1) : 0);  // spread chain warps over SMSPs
-        if (c <= c_hi && (warp % WPT) == cw) {
+        const int cw = (ts >> 1) & 1;  // spread the chain warps over the four SM sub-partitions
+        if (c <= c_hi && (warp % kWpt) == cw) {
           const int q = w - c;
           const int J = BETA ? NBv - 1 - q : q;
-          const int j = kBlk * J + lane;
-          const bool jin = j < L;
-          float pd[kBlk];
+          const int jbase = kBlk * J;
+          const int s = c * kRows + lane;                      // my row's step
+          const bool rowvalid = s < nsteps;
+          const int t = BETA ? Tn - 2 - s : 1 + s;
+          const float *utw = sm.ut + (size_t)ts * kBlk * kBlk;
+          float *iow = sm.io + (size_t)ts * kRows * kPitch + lane * kPitch;
+          const float *xbw = sm.xbuf + (size_t)ts * kRows * kPitch + lane * kPitch;
+          const int FI = sm.fbuf[ts * kRows + lane];
+          const float *rmax_blk = sm.rmax + jbase;
+
+          // predecessor sums formed from the previous chunk's last row (the "row -1" of this tile): lane ci
+          // computes column ci, handed to lane 0 column by column inside chain_column
+          float d0m = 0.f;
+          int d0f = kNegBig;
           {
-            const float *d = diag + (size_t)J * kBlk * kBlk + lane;
+            const float *pm = sm.stm + q * kBlk;
+            const int *pf = sm.stf + q * 4;
+            int f[4] = {pf[0], pf[1], pf[2], pf[3]};
+            float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int ii = 0; ii < kBlk; ii++) pd[ii] = __ldg(d + ii * kBlk);
+            for (int c4 = 0; c4 < kBlk; c4 += 4) {  // U[ci][lane] (row `lane` of the staged weights), 0 for ci >= lane
+              const float4 u4 = *reinterpret_cast<const float4 *>(utw + lane * kBlk + c4);
+              const float4 m4 = *reinterpret_cast<const float4 *>(pm + c4);
+              float s_ = ps[c4 >> 3];
+              s_ = fmaf(m4.x, u4.x, s_); s_ = fmaf(m4.y, u4.y, s_); s_ = fmaf(m4.z, u4.z, s_); s_ = fmaf(m4.w, u4.w, s_);
+              ps[c4 >> 3] = s_;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++) if (ps[g] > 0.f) d0f = max(d0f, f[g]);
+#pragma unroll
+            for (int g = 0; g < 4; g++) if (ps[g] > 0.f) d0m = fmaf(ps[g], pow2i(f[g] - d0f), d0m);
           }
-          const float rmj = sm.rmax[kBlk * J + lane];
-          const int sbeg = c * R, send = min(nsteps, sbeg + R);
-          const int tpf = BETA ? Tn - 1 - sbeg : sbeg;
-          float prev = jin ? lat[(int64_t)tpf * L + j] : ninf;
-          if (!BETA) prev += rmj;
-          float *ab = sm.abuf + warp * kBlk;
-          const float *xb = sm.xbuf + (size_t)ts * R * kBlk + lane;
-          const float *fb = sm.fbuf + ts * R;
-          // emission prefetch ring (4 steps ahead)
-          float mring[4];
+          float mant[kBlk];
+          int gexp[4] = {kNegBig, kNegBig, kNegBig, kNegBig};
+          int maxe = kNegBig;
+          chain_group<BETA, 0>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
+          chain_group<BETA, 8>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
+          chain_group<BETA, 16>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
+          chain_group<BETA, 24>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
+
+          // frame table entry of my row, chain state of the chunk's last valid row
+          if (rowvalid) sm.rmtab[t * NB + q] = maxe;
+          const int rl = min(kRows, nsteps - c * kRows) - 1;
+          if (lane == rl) {
 #pragma unroll
-          for (int p = 0; p < 4; p++) {
-            const int s = sbeg + p;
-            const int t = BETA ? Tn - 2 - s : 1 + s;
-            mring[p] = (s < send && jin) ? __ldg(match + (int64_t)t * L + j) : ninf;
+            for (int ci = 0; ci < kBlk; ci++) sm.stm[q * kBlk + ci] = mant[ci];
+#pragma unroll
+            for (int g = 0; g < 4; g++) sm.stf[q * 4 + g] = gexp[g];
           }
-          float g = warp_max_redux(prev);
-          for (int sb = sbeg; sb < send; sb += 4) {
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-              const int s = sb + p;
-              if (s < send) {
-                const int t = BETA ? Tn - 2 - s : 1 + s;
-                const float mt = mring[p];
-                {
-                  const int s4 = s + 4;
-                  const int t4 = BETA ? Tn - 2 - s4 : 1 + s4;
-                  mring[p] = (s4 < send && jin) ? __ldg(match + (int64_t)t4 * L + j) : ninf;
-                }
-                const float gs = (g > ninf) ? g : 0.f;
-                const float ah = exp2f((prev - gs) * kLog2e);
-                __syncwarp();
-                ab[lane] = ah;
-                __syncwarp();
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                for (int i4 = 0; i4 < kBlk; i4 += 4) {
-                  const float4 a4 = *reinterpret_cast<const float4 *>(ab + i4);
-                  s0 = fmaf(a4.x, pd[i4 + 0], s0); s1 = fmaf(a4.y, pd[i4 + 1], s1);
-                  s2 = fmaf(a4.z, pd[i4 + 2], s2); s3 = fmaf(a4.w, pd[i4 + 3], s3);
-                }
-                const float S = (s0 + s1) + (s2 + s3);
-                const int r = s - sbeg;
-                const float X = xb[r * kBlk];
-                const float f = fb[r];
-                const float Lm = fmaxf(f, g);
-                const float Ls = (Lm > ninf) ? Lm : 0.f;
-                const float ef = (f > ninf) ? exp2f((f - Ls) * kLog2e) : 0.f;
-                const float eg = (g > ninf) ? exp2f((gs - Ls) * kLog2e) : 0.f;
-                const float tot = fmaf(X, ef, S * eg);
-                const bool valid = jin && j >= t && j < O;
-                float out = ninf;
-                if (valid && tot > 0.f) out = (BETA ? mt + rmj : mt) + (Ls + __logf(tot));
-                if (jin) lat[(int64_t)t * L + j] = out;
-                prev = BETA ? out : out + rmj;
-                g = warp_max_redux(prev);
-                if (lane == 0) sm.rmtab[t * NB + q] = g;
-              }
+          __syncwarp();
+          // lattice values: coalesced row writes (lane = column)
+          const float *iot = sm.io + (size_t)ts * kRows * kPitch;
+          const int j = jbase + lane;
+          if (j < L) {
+            for (int rr = 0; rr <= rl; rr++) {
+              const int sr = c * kRows + rr;
+              const int tr = BETA ? Tn - 2 - sr : 1 + sr;
+              lat[(int64_t)tr * L + j] = iot[rr * kPitch + lane];
             }
           }
         }
       }
       __syncthreads();
+      if (dbg && threadIdx.x == 0 && blockIdx.x == 0) {
+        long long tdbg2 = clock64();
+        g_dp2_dbg[BETA ? 2 : 0] += tdbg1 - tdbg0;
+        g_dp2_dbg[BETA ? 3 : 1] += tdbg2 - tdbg1;
+      }
     }
   }
 }
 
-template <int R>
 __global__ void __launch_bounds__(kDp2Threads, 1)
 dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__restrict__ olen,
                               const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
                               const unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
-                              int32_t *__restrict__ status) {
+                              int32_t *__restrict__ status, int dbg) {
   extern __shared__ __align__(16) unsigned char dp2_smem[];
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
@@ -289,31 +449,33 @@ dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__
     return;
   }
   if (status && threadIdx.x == 0 && !is_beta) status[b] = DAGB200_ST_OK;
-  constexpr int TPW = kDp2Warps / (R / 16);
   Dp2Smem sm;
   float *p = reinterpret_cast<float *>(dp2_smem);
-  sm.xbuf = p;  p += TPW * R * kBlk;
-  sm.fbuf = p;  p += TPW * R;
-  sm.abuf = p;  p += kDp2Warps * kBlk;
+  sm.ut = p;    p += kTpw * kBlk * kBlk;
+  sm.xbuf = p;  p += kTpw * kRows * kPitch;
+  sm.io = p;    p += kTpw * kRows * kPitch;
+  sm.fbuf = reinterpret_cast<int *>(p);  p += kTpw * kRows;
   sm.rmax = p;  p += lay.NB * kBlk;
-  sm.rmtab = p;
+  sm.stm = p;   p += lay.NB * kBlk;
+  sm.stf = reinterpret_cast<int *>(p);  p += lay.NB * 4;
+  sm.rmtab = reinterpret_cast<int *>(p);
   const float *m = match + b * latsz;
   const unsigned char *wsb = ws + (size_t)b * lay.sample_bytes;
-  if (is_beta) blocked_chain<true, R>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl);
-  else blocked_chain<false, R>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl);
+  if (is_beta) blocked_chain<true>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg != 0);
+  else blocked_chain<false>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg != 0);
 }
 
-size_t dp2_smem_bytes(int R, int M, int L) {
+size_t dp2_smem_bytes(int M, int L) {
   TileLayout lay = TileLayout::make(L);
-  const int TPW = kDp2Warps / (R / 16);
-  return sizeof(float) * ((size_t)TPW * R * kBlk + (size_t)TPW * R + kDp2Warps * kBlk + (size_t)lay.NB * kBlk + (size_t)M * lay.NB);
+  return sizeof(float) * ((size_t)kTpw * kBlk * kBlk + 2 * (size_t)kTpw * kRows * kPitch + (size_t)kTpw * kRows +
+                          2 * (size_t)lay.NB * kBlk + (size_t)lay.NB * 4 + (size_t)M * lay.NB);
 }
 
 int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int L, int Tl, cudaStream_t st);
 
 size_t dp2_workspace_bytes(int B, int L) { return TileLayout::make(L).sample_bytes * (size_t)B; }
 
-bool dp2_supported(int M, int L) { return dp2_smem_bytes(64, M, L) <= 200 * 1024 && L >= 1; }
+bool dp2_supported(int M, int L) { return dp2_smem_bytes(M, L) <= 200 * 1024 && L >= 1; }
 
 int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
@@ -322,20 +484,18 @@ int launch_alpha_beta_blocked(const float *match, const float *links, const int6
   if (rc) return rc;
   TileLayout lay = TileLayout::make(L);
   dim3 grid(B, grad ? 2 : 1);
-  // rows per chunk: long targets amortise the transition tiles over 64 rows, short ones keep more waves
-  const int R = (M > 96) ? 64 : (M > 40 ? 32 : 16);
-  const size_t smem = dp2_smem_bytes(R, M, L);
-#define LAUNCH_DP2(RR)                                                                                          \
-  do {                                                                                                          \
-    cudaFuncSetAttribute(dag_alpha_beta_blocked_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    dag_alpha_beta_blocked_kernel<RR><<<grid, kDp2Threads, smem, st>>>(match, olen, tlen, alpha, beta,          \
-                                                                      (const unsigned char *)workspace, M, L, Tl, lay, status); \
-  } while (0)
-  if (R == 64) LAUNCH_DP2(64);
-  else if (R == 32) LAUNCH_DP2(32);
-  else LAUNCH_DP2(16);
-#undef LAUNCH_DP2
+  const size_t smem = dp2_smem_bytes(M, L);
+  static const bool dbg = getenv("DAGB200_DP2_DEBUG") != nullptr;
+  cudaFuncSetAttribute(dag_alpha_beta_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dag_alpha_beta_blocked_kernel<<<grid, kDp2Threads, smem, st>>>(match, olen, tlen, alpha, beta,
+                                                                (const unsigned char *)workspace, M, L, Tl, lay, status, dbg ? 1 : 0);
   DAGB200_CHECK_LAUNCH("dag_alpha_beta_blocked_kernel");
+  if (dbg) {
+    long long h[8];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, g_dp2_dbg, sizeof(h));
+    fprintf(stderr, "[dp2 dbg] cumulative cycles CTA0: alpha gemm %lld chain %lld | beta gemm %lld chain %lld\n", h[0], h[1], h[2], h[3]);
+  }
   return 0;
 }
 

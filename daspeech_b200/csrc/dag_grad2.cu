@@ -1,0 +1,239 @@
+// dag_grad2.cu -- transition gradient of the DAG loss as a tensor-core contraction, for sm_100a.
+//
+// Replaces calculate_grad_links_kernel (reference dag_loss.cu:432-485) on the fp32 path:
+//
+//   gl[b,i,k] = go[b] * sum_{t=0}^{Tn-2} exp(alpha[t,i] + beta[t+1,n] + links[i,k] - Z),   n = i+k+1
+//             = go[b] * exp(links[i,k] - Emax) * G[i,n],      G = A^T B  (contraction over the target index t)
+//   A[t,i] = exp(alpha[t,i] - u[t])            u[t]  = max over the LIVE (beta finite) vertices of the 128-block
+//   B[t,n] = exp(beta[t+1,n] + u[t] + Emax - Z)                Emax = max of the tile's transitions
+//
+// The reference spends one exp per (i,k,t) -- 8.4e9 at C2 -- walking alpha/beta down columns.  Here a CTA owns a
+// 128 x 128 (source x destination) tile, generates the two operand panels once per 16 target rows (1 exp per 64
+// MACs), splits them into bf16 hi/lo (3 mma.sync.m16n8k16 per product, ~2^-16 relative error, fp32 accumulation)
+// and multiplies by exp(links) in the epilogue while streaming the links tile and writing grad_links once,
+// coalesced, including the zero padding.
+//
+// Dynamic range: alpha spans > 87 nats inside a 128-vertex window on tight lattices, so the operands are stacked
+// along K in two exponent levels 60 nats apart (A level 1 holds exp(x+60) for x < -60, B level 1 holds
+// exp(y-60)); the level cancels inside each product.  Usable window: 147 nats below the best live vertex.
+#include "common.cuh"
+
+namespace dagb200 {
+
+constexpr int kG2Tile = 128;
+constexpr int kG2Threads = 256;
+constexpr int kG2Kc = 16;            // target rows per K chunk
+constexpr int kG2Pitch = 136;        // bf16 elements per operand row (128 + 8: conflict-free ldmatrix)
+constexpr int kG2CPitch = 132;       // floats per row of the staged output tile
+constexpr float kG2Level = 60.f;
+
+__device__ __forceinline__ void mma_bf16_g2(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *smem_ptr) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+struct G2Planes {            // [level][hi/lo][kG2Kc][kG2Pitch]
+  __nv_bfloat16 v[2][2][kG2Kc][kG2Pitch];
+};
+
+__global__ void __launch_bounds__(kG2Threads)
+grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ alpha, const float *__restrict__ beta,
+                      const float *__restrict__ links, const int64_t *__restrict__ olen,
+                      const int64_t *__restrict__ tlen, float *__restrict__ gl, int M, int L, int Tl, int NI) {
+  extern __shared__ __align__(16) unsigned char g2_smem[];
+  const int b = blockIdx.y;
+  const int I = blockIdx.x / NI, J = blockIdx.x % NI;
+  if (J < I) return;
+  const int i0 = I * kG2Tile, n0 = J * kG2Tile;
+  if (n0 - (i0 + kG2Tile - 1) - 1 >= Tl) return;       // tile entirely beyond the transition band: no storage
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int O = (int)olen[b], Tn = (int)tlen[b];
+  const int64_t lat = (int64_t)M * L;
+  const float *a = alpha + b * lat, *be = beta + b * lat;
+  const float *E = links + (int64_t)b * L * Tl;
+  float *g = gl + (int64_t)b * L * Tl;
+  const float Z = be[0];
+  const float gout = go[b];
+  const float ninf = neg_inf_f();
+  const bool dead = isinf(Z) || O > L || Tn > M || Tn < 2 || O < 2;
+
+  // carve shared memory: operand staging (aliased by the output tile after the K loop)
+  float *stage_a = reinterpret_cast<float *>(g2_smem);            // [16][128]
+  float *stage_bi = stage_a + kG2Kc * kG2Tile;                    // [16][128]
+  float *stage_bn = stage_bi + kG2Kc * kG2Tile;                   // [16][128]
+  float *u_s = stage_bn + kG2Kc * kG2Tile;                        // [16] (+ padding to 32)
+  float *red_s = u_s + 16;                                        // [16]
+  G2Planes *pa = reinterpret_cast<G2Planes *>(u_s + 32);
+  G2Planes *pb = pa + 1;
+  float *cs = reinterpret_cast<float *>(g2_smem);                 // [128][kG2CPitch] after the loop
+
+  // ---- tile maximum of the transitions (valid entries only) -------------------------------------------
+  bool compute = !dead && i0 < O && n0 < O && (n0 + kG2Tile - 1 > i0);
+  float emax = ninf;
+  if (compute) {
+    for (int ii = warp; ii < kG2Tile; ii += kG2Threads / 32) {
+      const int i = i0 + ii;
+      if (i >= O) break;
+      const int klo = max(0, n0 - i - 1), khi = min(min(Tl, n0 + kG2Tile - i - 1), O - i - 1);
+      const float *row = E + (int64_t)i * Tl;
+      for (int k = klo + lane; k < khi; k += 32) emax = fmaxf(emax, __ldg(row + k));
+    }
+    emax = warp_max(emax);
+    if (lane == 0) red_s[warp] = emax;
+    __syncthreads();
+    emax = red_s[0];
+#pragma unroll
+    for (int w = 1; w < kG2Threads / 32; w++) emax = fmaxf(emax, red_s[w]);
+    __syncthreads();
+    if (emax == ninf) compute = false;   // no usable transition in this tile
+  }
+
+  float acc[4][4][4];
+#pragma unroll
+  for (int x = 0; x < 4; x++)
+#pragma unroll
+    for (int y = 0; y < 4; y++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[x][y][e] = 0.f;
+
+  if (compute) {
+    const int wi = warp >> 2, wn = warp & 3;     // warp tile: 64 sources x 32 destinations
+    const int nsteps = Tn - 1;
+    const float shift = emax - Z;
+    for (int t0 = 0; t0 < nsteps; t0 += kG2Kc) {
+      // stage alpha[t][i-block], beta[t][i-block] (liveness) and beta[t+1][n-block], coalesced rows
+      for (int x = tid; x < kG2Kc * kG2Tile; x += kG2Threads) {
+        const int tr = x >> 7, c = x & 127;
+        const int t = t0 + tr;
+        const bool tv = t < nsteps;
+        const int i = i0 + c, n = n0 + c;
+        stage_a[x] = (tv && i < O) ? a[(int64_t)t * L + i] : ninf;
+        stage_bi[x] = (tv && i < O) ? be[(int64_t)t * L + i] : ninf;
+        stage_bn[x] = (tv && n < O) ? be[(int64_t)(t + 1) * L + n] : ninf;
+      }
+      __syncthreads();
+      // frame u[t] = max alpha over live vertices of the block (2 rows per warp)
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        const int tr = warp * 2 + rr;
+        float m = ninf;
+#pragma unroll
+        for (int c = lane; c < kG2Tile; c += 32)
+          if (stage_bi[tr * kG2Tile + c] > ninf) m = fmaxf(m, stage_a[tr * kG2Tile + c]);
+        m = warp_max(m);
+        if (lane == 0) u_s[tr] = m;
+      }
+      __syncthreads();
+      // operand planes: two exponent levels, bf16 hi/lo
+      for (int x = tid; x < kG2Kc * kG2Tile; x += kG2Threads) {
+        const int tr = x >> 7, c = x & 127;
+        const float u = u_s[tr];
+        float a0v = 0.f, a1v = 0.f, b0v = 0.f, b1v = 0.f;
+        if (u > ninf) {
+          const float xa = (stage_bi[x] > ninf) ? stage_a[x] - u : ninf;
+          if (xa >= -kG2Level) a0v = __expf(xa);
+          else if (xa > ninf) a1v = __expf(xa + kG2Level);
+          const float y = stage_bn[x] + u + shift;
+          if (y > ninf) {
+            b0v = __expf(fminf(y, 80.f));
+            b1v = __expf(fminf(y - kG2Level, 80.f));
+          }
+        }
+        const __nv_bfloat16 a0h = __float2bfloat16_rn(a0v), a1h = __float2bfloat16_rn(a1v);
+        const __nv_bfloat16 b0h = __float2bfloat16_rn(b0v), b1h = __float2bfloat16_rn(b1v);
+        pa->v[0][0][tr][c] = a0h; pa->v[0][1][tr][c] = __float2bfloat16_rn(a0v - __bfloat162float(a0h));
+        pa->v[1][0][tr][c] = a1h; pa->v[1][1][tr][c] = __float2bfloat16_rn(a1v - __bfloat162float(a1h));
+        pb->v[0][0][tr][c] = b0h; pb->v[0][1][tr][c] = __float2bfloat16_rn(b0v - __bfloat162float(b0h));
+        pb->v[1][0][tr][c] = b1h; pb->v[1][1][tr][c] = __float2bfloat16_rn(b1v - __bfloat162float(b1h));
+      }
+      __syncthreads();
+      // tensor-core contraction over the 16 rows of this chunk (x2 levels, x3 split products)
+#pragma unroll
+      for (int lev = 0; lev < 2; lev++) {
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int np = 0; np < 2; np++) {
+          const int nb = 32 * wn + 16 * np;
+          const int krow = ((lane >> 3) & 1) * 8 + (lane & 7), ncol = nb + (lane >> 4) * 8;
+          uint32_t r[4];
+          ldmatrix_x4_trans(r, &pb->v[lev][0][krow][ncol]);
+          bh[2 * np][0] = r[0]; bh[2 * np][1] = r[1]; bh[2 * np + 1][0] = r[2]; bh[2 * np + 1][1] = r[3];
+          ldmatrix_x4_trans(r, &pb->v[lev][1][krow][ncol]);
+          bl[2 * np][0] = r[0]; bl[2 * np][1] = r[1]; bl[2 * np + 1][0] = r[2]; bl[2 * np + 1][1] = r[3];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          const int mb = 64 * wi + 16 * mt;
+          const int krow = (lane >> 4) * 8 + (lane & 7), mcol = mb + ((lane >> 3) & 1) * 8;
+          uint32_t ah[4], al[4];
+          ldmatrix_x4_trans(ah, &pa->v[lev][0][krow][mcol]);
+          ldmatrix_x4_trans(al, &pa->v[lev][1][krow][mcol]);
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            mma_bf16_g2(acc[mt][nt], ah, bh[nt][0], bh[nt][1]);
+            mma_bf16_g2(acc[mt][nt], al, bh[nt][0], bh[nt][1]);
+            mma_bf16_g2(acc[mt][nt], ah, bl[nt][0], bl[nt][1]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // stage the output tile (aliases the operand buffers: all warps are past the last barrier)
+    const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) {
+        const int m = 64 * wi + 16 * mt + gid, n = 32 * wn + 8 * nt + 2 * tig;
+        *reinterpret_cast<float2 *>(cs + m * kG2CPitch + n) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+        *reinterpret_cast<float2 *>(cs + (m + 8) * kG2CPitch + n) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+      }
+    __syncthreads();
+  }
+
+  // ---- epilogue: gl = go * exp(links - Emax) * G, one coalesced write per row, zeros elsewhere -----------
+  const bool last_col = (n0 + kG2Tile >= L);
+  for (int ii = warp; ii < kG2Tile; ii += kG2Threads / 32) {
+    const int i = i0 + ii;
+    if (i >= L) break;
+    const float *erow = E + (int64_t)i * Tl;
+    float *grow = g + (int64_t)i * Tl;
+    for (int nn = lane; nn < kG2Tile; nn += 32) {
+      const int n = n0 + nn, k = n - i - 1;
+      if (k < 0 || k >= Tl) continue;
+      float v = 0.f;
+      if (compute && i < O && n < O) v = gout * __expf(__ldg(erow + k) - emax) * cs[ii * kG2CPitch + nn];
+      grow[k] = v;
+    }
+    if (last_col) {  // transitions that point beyond the padded graph: k >= L-1-i
+      for (int k = max(0, n0 + kG2Tile - i - 1) + lane; k < Tl; k += 32) grow[k] = 0.f;
+    }
+  }
+}
+
+size_t g2_smem_bytes() {
+  const size_t stage = sizeof(float) * (3 * kG2Kc * kG2Tile + 32) + 2 * sizeof(G2Planes);
+  const size_t cst = sizeof(float) * kG2Tile * kG2CPitch;
+  return stage > cst ? stage : cst;
+}
+
+int launch_grad_links_mma(const float *go, const float *alpha, const float *beta, const float *links,
+                          const int64_t *olen, const int64_t *tlen, float *gl, int B, int M, int L, int Tl,
+                          cudaStream_t st) {
+  const int NI = (L + kG2Tile - 1) / kG2Tile;
+  const size_t smem = g2_smem_bytes();
+  cudaFuncSetAttribute(grad_links_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(NI * NI, B);
+  grad_links_mma_kernel<<<grid, kG2Threads, smem, st>>>(go, alpha, beta, links, olen, tlen, gl, M, L, Tl, NI);
+  DAGB200_CHECK_LAUNCH("grad_links_mma_kernel");
+  return 0;
+}
+
+}  // namespace dagb200

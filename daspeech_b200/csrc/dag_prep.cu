@@ -67,9 +67,11 @@ dag_prep_kernel(const float *__restrict__ links, const int64_t *__restrict__ ole
     if (J == I) {
       float *dA = reinterpret_cast<float *>(base + lay.off_diagA) + (size_t)I * kBlk * kBlk;
       float *dB = reinterpret_cast<float *>(base + lay.off_diagB) + (size_t)I * kBlk * kBlk;
+      // [cj][ci] = weight of in-block predecessor ci for cell cj, both in sweep order (alpha: ascending vertex,
+      // beta: descending vertex), zero for ci >= cj
       for (int r = warp; r < kBlk; r += 8) {
-        dA[r * kBlk + lane] = tile[r][lane];   // [ii][jj]
-        dB[r * kBlk + lane] = tile[lane][r];   // [nn][jj] = P'[jj][nn]
+        dA[r * kBlk + lane] = tile[lane][r];                       // P'[ci][cj]
+        dB[r * kBlk + lane] = tile[kBlk - 1 - r][kBlk - 1 - lane];  // P'[31-cj][31-ci]
       }
     } else {
       const int q = warp;  // 8 warps <-> 8 units

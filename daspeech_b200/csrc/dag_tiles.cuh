@@ -3,8 +3,8 @@
 //
 // Vertices are grouped in blocks of 32.  For every utterance the scratch holds, for NB = ceil(L/32):
 //   rmax  [NB*32]            per-source-vertex max_k links[i][k] over valid successors (-inf if none)
-//   diagA [NB][32][32] fp32  P'[32J+ii][32J+jj]            (row ii, lane jj)   -- alpha chain, strictly upper
-//   diagB [NB][32][32] fp32  P'[32J+jj][32J+nn] at [nn][jj] (row nn, lane jj)  -- beta chain
+//   diagA [NB][32][32] fp32  [cj][ci] = P'[32J+ci][32J+cj]        in-block predecessor weights of the alpha chain
+//   diagB [NB][32][32] fp32  [cj][ci] = P'[32J+31-cj][32J+31-ci]  the same for beta, in its (descending) sweep order
 //   tilesA[NB(NB-1)/2] 4 KB  off-diagonal tile (I<J) as the B operand of mma.m16n8k16 with K = source vertex,
 //                            N = destination vertex, bf16 hi plane then bf16 lo plane, in FRAGMENT order
 //   tilesB[NB(NB-1)/2] 4 KB  the same tile as the B operand with K = destination vertex, N = source vertex

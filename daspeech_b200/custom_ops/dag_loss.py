@@ -129,6 +129,7 @@ class _DagKernel:
         links = links.contiguous()
         grad_match_all = torch.empty_like(alpha)
         grad_links = torch.empty((bsz, prelen, translen), dtype=match_all.dtype, device=match_all.device)
+        self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(match_all.device):
             rc = self.lib.dagb200_dag_loss_backward(_ptr(grad_output), _ptr(alpha), _ptr(beta), _ptr(match_all),
                                                     _ptr(links), _ptr(output_length), _ptr(target_length),

@@ -56,6 +56,11 @@ extern "C" {
 int dagb200_version(void);
 const char *dagb200_last_error(void);
 
+/* Process-wide switch: 1 = always run the exact log-domain kernels (one exp per lattice edge, the reference's
+ * arithmetic); 0 (default) = blocked tensor-core kernels for fp32 lattices (flush-to-zero contract). */
+void dagb200_set_exact(int on);
+int dagb200_get_exact(void);
+
 /* Replaces `logsoftmax_gather` (dag_loss.cpp:22, logsoftmax_gather.cu:313-377).
  *   logits  [B][L][V] contiguous, dtype F32/F16/BF16/F64; OVERWRITTEN with softmax probabilities
  *           iff require_gradient != 0 (the reference's in-place contract, dag_loss.py:272-274)
