@@ -405,9 +405,18 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
                                    (double *)alpha, (double *)beta, B, M, L, T, grad, status, st);
 }
 
+namespace dagb200 {
+bool vit2_supported(int M, int L);
+int launch_viterbi_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
+                           float *lattice, uint16_t *trace, int32_t *path, int B, int M, int L, int Tl,
+                           int32_t *status, cudaStream_t st);
+}  // namespace dagb200
+
+// trace (uint16 per cell) + a lattice plane for the case the caller does not want alpha back
 extern "C" size_t dagb200_best_alignment_workspace_bytes(int B, int M, int L, int T) {
   (void)T;
-  return (size_t)B * M * L * sizeof(uint16_t);
+  const size_t cells = (size_t)B * M * L;
+  return ((cells * sizeof(uint16_t) + 255) & ~(size_t)255) + cells * sizeof(float);
 }
 
 extern "C" int dagb200_dag_best_alignment(const void *match, const void *links, const int64_t *output_length,
@@ -423,6 +432,13 @@ extern "C" int dagb200_dag_best_alignment(const void *match, const void *links, 
                     DAGB200_EWORKSPACE, "dag_best_alignment: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int wbits = config + 1;  // config 1..4 -> TRANS_BLOCK_SIZE 4/8/16/32 (dag_best_alignment.cu:243-246)
+  if (dtype == DAGB200_F32 && config == 1 && !g_exact_mode && vit2_supported(M, L)) {
+    const size_t cells = (size_t)B * M * L;
+    float *lattice = alpha ? (float *)alpha
+                           : reinterpret_cast<float *>((unsigned char *)workspace + ((cells * sizeof(uint16_t) + 255) & ~(size_t)255));
+    return launch_viterbi_blocked((const float *)match, (const float *)links, output_length, target_length, lattice,
+                                  (uint16_t *)workspace, path, B, M, L, T, status, st);
+  }
   if (dtype == DAGB200_F32)
     return launch_viterbi<float>((const float *)match, (const float *)links, output_length, target_length,
                                  (float *)alpha, (uint16_t *)workspace, path, B, M, L, T, wbits, status, st);

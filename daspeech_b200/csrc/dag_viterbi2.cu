@@ -1,0 +1,364 @@
+// dag_viterbi2.cu -- blocked max-plus (Viterbi) recurrence with back-pointers, for sm_100a.
+//
+// Replaces calculate_maxalpha_kernel + calculate_backtrace_kernel (reference dag_best_alignment.cu:39-130,
+// 170-185) on the fp32 / config 1 path.  Arithmetic is the reference's, operation for operation: a candidate is
+// ONE fp32 add (previous value + transition), the cell value one more add (+ emission), so lattice values are
+// bit-identical; the arg-max reproduces the reference's tie-break (TRANS_BLOCK_SIZE = 4: candidate delta lives in
+// lane (delta-1)%4, a lane keeps its first strict maximum = smallest delta, lanes merge with priority 0,2,1,3)
+// without ever comparing keys in the inner loop:
+//   * candidates are visited in DESCENDING delta and kept in four per-class maxima updated with '>=', so inside a
+//     class the smallest delta wins; classes are then merged in priority order with strict '>'.
+// Organisation = dag_dp2.cu: vertices in blocks of 32, rows in chunks of 32, anti-diagonal waves inside one CTA
+// per utterance.  Far predecessors: lanes = destination columns, the 32x32 transition tile column lives in
+// registers and is reused for 16 rows (the reference re-reads every transition for every row); near
+// predecessors: lanes = rows, serial sweep over the 32 columns, one shuffle per column.
+#include "common.cuh"
+
+namespace dagb200 {
+
+constexpr int kV2Threads = 512;
+constexpr int kV2Warps = kV2Threads / 32;
+constexpr int kV2Tpw = kV2Warps / 2;      // tiles per batch (2 warps x 16 rows per tile in the far phase)
+constexpr int kV2Pitch = 33;
+constexpr int kVB = 32;
+
+__device__ __forceinline__ int rank4(int delta) {  // priority of the class of `delta`: classes 0,2,1,3 -> 0,1,2,3
+  const int cl = (delta - 1) & 3;
+  return ((cl & 1) << 1) | (cl >> 1);
+}
+// is candidate (v1, d1) preferred over (v2, d2)?  (-inf never wins)
+__device__ __forceinline__ bool better(float v1, int d1, float v2, int d2) {
+  if (v1 > v2) return true;
+  if (v1 < v2 || !(v1 > neg_inf_f())) return false;
+  const int r1 = rank4(d1), r2 = rank4(d2);
+  return r1 < r2 || (r1 == r2 && d1 < d2);
+}
+__device__ __forceinline__ void cp_async_f32_v(float *smem_dst, const float *gsrc) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gsrc) : "memory");
+}
+
+struct V2Smem {
+  float *xv;     // [tiles][32][pitch] best far candidate value per (row, column)
+  int *xd;       // [tiles][32][pitch] its delta; overwritten column by column with the chosen delta (trace)
+  float *ed;     // [tiles][32][32]    diagonal transition block, [cj][ci]
+  float *io;     // [tiles][32][pitch] emissions in, cell values out
+  float *vs;     // [warps][16][32]    previous-row values of the current source block (far phase)
+  unsigned char *flag;  // [M][NB]     1 if block row has a finite value
+};
+
+// one column of the diagonal sweep (lanes = rows)
+template <int CJ>
+__device__ __forceinline__ void vit_column(float (&vrow)[kVB], const float *edw, const float (&mm)[8], float *iow,
+                                           const float *xvw, int *xdw, int lane, float d0v, int d0d,
+                                           bool rowvalid, int jbase, int t, int O, bool &anyfin) {
+  const float ninf = neg_inf_f();
+  // best in-block predecessor of MY row for the next row's column CJ; classes are compile-time here
+  float bv[4] = {ninf, ninf, ninf, ninf};
+  int bd[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int c4 = 0; c4 < CJ; c4 += 4) {
+    const float4 e4 = *reinterpret_cast<const float4 *>(edw + CJ * kVB + c4);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int ci = c4 + k;
+      if (ci < CJ) {
+        const int delta = CJ - ci, cl = (delta - 1) & 3;
+        const float x = vrow[ci] + (k == 0 ? e4.x : k == 1 ? e4.y : k == 2 ? e4.z : e4.w);
+        if (x >= bv[cl]) { bv[cl] = x; bd[cl] = delta; }   // descending delta: later = smaller delta wins ties
+      }
+    }
+  }
+  float nv = bv[0]; int nd = bd[0];
+  if (bv[2] > nv) { nv = bv[2]; nd = bd[2]; }
+  if (bv[1] > nv) { nv = bv[1]; nd = bd[1]; }
+  if (bv[3] > nv) { nv = bv[3]; nd = bd[3]; }
+  // hand to the next row
+  float rv = __shfl_up_sync(0xffffffffu, nv, 1);
+  int rd = __shfl_up_sync(0xffffffffu, nd, 1);
+  const float zv = __shfl_sync(0xffffffffu, d0v, CJ);
+  const int zd = __shfl_sync(0xffffffffu, d0d, CJ);
+  if (lane == 0) { rv = zv; rd = zd; }
+  // merge with the far candidate
+  const float fv = xvw[CJ];
+  const int fd = xdw[CJ];
+  float best = fv; int bdl = fd;
+  if (better(rv, rd, fv, fd)) { best = rv; bdl = rd; }
+  const int j = jbase + CJ;
+  const bool valid = rowvalid && j >= t && j < O;
+  float val = ninf; int dl = 0;
+  if (valid) {
+    val = best + mm[CJ & 7];
+    if (best > ninf) dl = bdl;
+  }
+  vrow[CJ] = val;
+  iow[CJ] = val;
+  xdw[CJ] = dl;
+  anyfin = anyfin || (val > ninf);
+}
+
+template <int CJ0>
+__device__ __forceinline__ void vit_group(float (&vrow)[kVB], const float *edw, float *iow, const float *xvw,
+                                          int *xdw, int lane, float d0v, int d0d, bool rowvalid, int jbase, int t,
+                                          int O, bool &anyfin) {
+  float mm[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) mm[k] = iow[CJ0 + k];
+  vit_column<CJ0 + 0>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 1>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 2>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 3>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 4>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 5>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 6>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+  vit_column<CJ0 + 7>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+}
+
+__global__ void __launch_bounds__(kV2Threads, 1)
+dag_viterbi_blocked_kernel(const float *__restrict__ match, const float *__restrict__ links,
+                           const int64_t *__restrict__ olen, const int64_t *__restrict__ tlen,
+                           float *__restrict__ lattice, uint16_t *__restrict__ trace, int32_t *__restrict__ path,
+                           int M, int L, int Tl, int NB, int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char v2_smem[];
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int O = (int)olen[b], Tn = (int)tlen[b];
+  const int64_t latsz = (int64_t)M * L;
+  const float ninf = neg_inf_f();
+  float *lat = lattice + b * latsz;
+  uint16_t *trg = trace + b * latsz;
+  int32_t *prow = path + (int64_t)b * L;
+  const float *m = match + b * latsz;
+  const float *E = links + (int64_t)b * L * Tl;
+  for (int j = threadIdx.x; j < L; j += kV2Threads) prow[j] = -1;
+
+  int st = DAGB200_ST_OK;
+  if (Tn < 2 || O < 2) st = DAGB200_ST_LEN_LT2;
+  else if (O < Tn || O > L || Tn > M) st = DAGB200_ST_GRAPH_SMALL;
+  else if ((int64_t)(Tn - 1) * Tl + 1 < O) st = DAGB200_ST_TOO_SHORT;
+  if (st != DAGB200_ST_OK) {
+    for (int64_t x = threadIdx.x; x < latsz; x += kV2Threads) lat[x] = ninf;
+    if (status && threadIdx.x == 0) status[b] = st;
+    return;
+  }
+
+  V2Smem sm;
+  {
+    float *p = reinterpret_cast<float *>(v2_smem);
+    sm.ed = p;  p += kV2Tpw * kVB * kVB;
+    sm.xv = p;  p += kV2Tpw * kVB * kV2Pitch;
+    sm.xd = reinterpret_cast<int *>(p);  p += kV2Tpw * kVB * kV2Pitch;
+    sm.io = p;  p += kV2Tpw * kVB * kV2Pitch;
+    sm.vs = p;  p += kV2Warps * 16 * kVB;
+    sm.flag = reinterpret_cast<unsigned char *>(p);
+  }
+  const int NBv = (O + kVB - 1) / kVB;
+  const int nsteps = Tn - 1;
+  const int NCv = (nsteps + kVB - 1) / kVB;
+  const int band = 1 + (Tl - 1) / kVB;
+
+  // prologue: padding, seed row, flags
+  for (int x = threadIdx.x; x < M * NB; x += kV2Threads) sm.flag[x] = 0;
+  {
+    const int64_t tail0 = (int64_t)Tn * L;
+    for (int64_t x = tail0 + threadIdx.x; x < latsz; x += kV2Threads) lat[x] = ninf;
+    const int c0 = NBv * kVB;
+    if (c0 < L) {
+      const int wcols = L - c0;
+      for (int x = threadIdx.x; x < Tn * wcols; x += kV2Threads) lat[(int64_t)(x / wcols) * L + c0 + x % wcols] = ninf;
+    }
+    for (int j = threadIdx.x; j < min(L, c0); j += kV2Threads) lat[j] = (j == 0) ? m[0] : ninf;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && m[0] > ninf) sm.flag[0] = 1;
+  __syncthreads();
+
+  const int nwaves = NBv + NCv - 1;
+  for (int w = 0; w < nwaves; w++) {
+    const int c_lo = max(0, w - NBv + 1), c_hi = min(NCv - 1, w);
+    for (int cb = c_lo; cb <= c_hi; cb += kV2Tpw) {
+      // ======================= far phase: lanes = destination columns, 16 rows per warp =======================
+      {
+        const int ts = warp >> 1, sl = warp & 1;
+        const int c = cb + ts;
+        if (c <= c_hi) {
+          const int J = w - c;
+          const int j = kVB * J + lane;
+          // stage the diagonal transition block ([cj][ci]) and the emissions of this tile asynchronously
+          {
+            float *edw = sm.ed + (size_t)ts * kVB * kVB;
+            float *iow = sm.io + (size_t)ts * kVB * kV2Pitch;
+            for (int rr = sl; rr < kVB; rr += 2) {
+              // row rr of the diagonal block = source vertex ci = rr, lane = destination cj
+              const int i = kVB * J + rr, k = lane - rr - 1;
+              if (k >= 0 && k < Tl && i < O && j < O) cp_async_f32_v(edw + lane * kVB + rr, E + (int64_t)i * Tl + k);
+              else edw[lane * kVB + rr] = ninf;
+              const int s = c * kVB + rr;
+              if (s < nsteps && j < L) cp_async_f32_v(iow + rr * kV2Pitch + lane, m + (int64_t)(1 + s) * L + j);
+              else iow[rr * kV2Pitch + lane] = ninf;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
+          float *xvw = sm.xv + (size_t)ts * kVB * kV2Pitch + (16 * sl) * kV2Pitch + lane;
+          int *xdw = sm.xd + (size_t)ts * kVB * kV2Pitch + (16 * sl) * kV2Pitch + lane;
+#pragma unroll
+          for (int rr = 0; rr < 16; rr++) { xvw[rr * kV2Pitch] = ninf; xdw[rr * kV2Pitch] = 0; }
+          float *vsw = sm.vs + (size_t)warp * 16 * kVB;
+          const int s_first = c * kVB + 16 * sl;           // previous-row index of my first row
+          const int qlo = max(0, J - band);
+          for (int I = qlo; I < J; I++) {
+            // skip source blocks without a finite value on any of my 16 previous rows
+            bool any = false;
+            if (lane < 16 && s_first + lane < nsteps) any = sm.flag[(s_first + lane) * NB + I] != 0;
+            if (!__any_sync(0xffffffffu, any)) continue;
+            // my column of the transition tile: E[32I+ii][j - (32I+ii) - 1]
+            float ecol[kVB];
+#pragma unroll
+            for (int ii = 0; ii < kVB; ii++) {
+              const int i = kVB * I + ii, k = j - i - 1;
+              ecol[ii] = (k < Tl && j < O) ? __ldg(E + (int64_t)i * Tl + k) : ninf;   // i < 32J <= O always here
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int rr = 0; rr < 16; rr++) {
+              const int tp = s_first + rr;
+              vsw[rr * kVB + lane] = (tp < nsteps) ? lat[(int64_t)tp * L + kVB * I + lane] : ninf;
+            }
+            __syncwarp();
+            const int dbase = kVB * (J - I) + lane;        // delta of source ii is dbase - ii
+            // class of slot u = ii & 3 for this lane: (dbase - u - 1) & 3 ; merge order = priority 0,2,1,3
+            int ord[4];   // ord[r] = slot whose class has priority r: class = bitrev2(r), slot = (dbase-1-class) & 3
+#pragma unroll
+            for (int r4 = 0; r4 < 4; r4++) ord[r4] = (dbase - 1 - (((r4 & 1) << 1) | (r4 >> 1))) & 3;
+            for (int rr = 0; rr < 16; rr++) {
+              float bv0 = ninf, bv1 = ninf, bv2 = ninf, bv3 = ninf;
+              int bi0 = 0, bi1 = 0, bi2 = 0, bi3 = 0;
+#pragma unroll
+              for (int c4 = 0; c4 < kVB; c4 += 4) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
+                float x;
+                x = a4.x + ecol[c4 + 0]; if (x >= bv0) { bv0 = x; bi0 = c4 + 0; }
+                x = a4.y + ecol[c4 + 1]; if (x >= bv1) { bv1 = x; bi1 = c4 + 1; }
+                x = a4.z + ecol[c4 + 2]; if (x >= bv2) { bv2 = x; bi2 = c4 + 2; }
+                x = a4.w + ecol[c4 + 3]; if (x >= bv3) { bv3 = x; bi3 = c4 + 3; }
+              }
+              const float bvs[4] = {bv0, bv1, bv2, bv3};
+              const int bis[4] = {bi0, bi1, bi2, bi3};
+              // slots in priority order, strict '>'
+              float nv = ninf; int ni = 0;
+#pragma unroll
+              for (int r4 = 0; r4 < 4; r4++) {
+                const int u = ord[r4];
+                const float v = (u == 0) ? bvs[0] : (u == 1) ? bvs[1] : (u == 2) ? bvs[2] : bvs[3];
+                const int ii = (u == 0) ? bis[0] : (u == 1) ? bis[1] : (u == 2) ? bis[2] : bis[3];
+                if (r4 == 0 || v > nv) { nv = v; ni = ii; }
+              }
+              const int nd = dbase - ni;
+              const float rv = xvw[rr * kV2Pitch];
+              const int rd = xdw[rr * kV2Pitch];
+              // this block is nearer than everything accumulated so far: it wins ties unless its class ranks lower
+              if (nv > rv || (nv == rv && nv > ninf && rank4(nd) <= rank4(rd))) {
+                xvw[rr * kV2Pitch] = nv;
+                xdw[rr * kV2Pitch] = nd;
+              }
+            }
+          }
+          asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+      }
+      __syncthreads();
+      // ======================= chain phase: lanes = rows, serial over the 32 columns =======================
+      {
+        const int ts = warp >> 1;
+        const int c = cb + ts;
+        const int cw = (ts >> 1) & 1;
+        if (c <= c_hi && (warp & 1) == cw) {
+          const int J = w - c;
+          const int jbase = kVB * J;
+          const int s = c * kVB + lane;
+          const bool rowvalid = s < nsteps;
+          const int t = 1 + s;
+          const float *edw = sm.ed + (size_t)ts * kVB * kVB;
+          float *iow = sm.io + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          const float *xvw = sm.xv + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          int *xdw = sm.xd + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          // "row -1": best in-block predecessor formed from the last row of the previous chunk; lane = column
+          float d0v = ninf; int d0d = 0;
+          {
+            const int tp = c * kVB;   // previous-row index of the chunk's first row
+            const float pv = (jbase + lane < L) ? lat[(int64_t)tp * L + jbase + lane] : ninf;
+            for (int c4 = 0; c4 < kVB; c4 += 4) {   // any order: `better` is a total order
+              const float4 e4 = *reinterpret_cast<const float4 *>(edw + lane * kVB + c4);   // -inf for ci >= lane
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int ci = c4 + k;
+                const float x = __shfl_sync(0xffffffffu, pv, ci) + (k == 0 ? e4.x : k == 1 ? e4.y : k == 2 ? e4.z : e4.w);
+                const int delta = lane - ci;
+                if (ci < lane && better(x, delta, d0v, d0d)) { d0v = x; d0d = delta; }
+              }
+            }
+          }
+          float vrow[kVB];
+          bool anyfin = false;
+          vit_group<0>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vit_group<8>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vit_group<16>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vit_group<24>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          if (rowvalid) sm.flag[t * NB + J] = anyfin ? 1 : 0;
+          __syncwarp();
+          // coalesced writes of the tile: cell values and back-pointers (lane = column)
+          const int rl = min(kVB, nsteps - c * kVB) - 1;
+          const float *iot = sm.io + (size_t)ts * kVB * kV2Pitch;
+          const int *trt = sm.xd + (size_t)ts * kVB * kV2Pitch;
+          const int j = jbase + lane;
+          if (j < L) {
+            for (int rr = 0; rr <= rl; rr++) {
+              const int64_t off = (int64_t)(1 + c * kVB + rr) * L + j;
+              lat[off] = iot[rr * kV2Pitch + lane];
+              trg[off] = (uint16_t)trt[rr * kV2Pitch + lane];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // backtrace (dag_best_alignment.cu:178-184)
+  if (threadIdx.x == 0) {
+    int code = DAGB200_ST_OK;
+    if (!(lat[(int64_t)(Tn - 1) * L + O - 1] > ninf)) {
+      code = DAGB200_ST_NO_PATH;
+    } else {
+      int pos = O - 1;
+      for (int i = Tn - 1; i >= 0; i--) {
+        prow[pos] = i;
+        if (i == 0) break;
+        const int d = trg[(int64_t)i * L + pos];
+        if (d == 0) { code = DAGB200_ST_NO_PATH; break; }
+        pos -= d;
+      }
+    }
+    if (status) status[b] = code;
+  }
+}
+
+size_t vit2_smem_bytes(int M, int L) {
+  const int NB = (L + kVB - 1) / kVB;
+  return sizeof(float) * ((size_t)kV2Tpw * kVB * kVB + 3 * (size_t)kV2Tpw * kVB * kV2Pitch + (size_t)kV2Warps * 16 * kVB) +
+         (size_t)M * NB + 16;
+}
+bool vit2_supported(int M, int L) { return vit2_smem_bytes(M, L) <= 200 * 1024; }
+
+int launch_viterbi_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
+                           float *lattice, uint16_t *trace, int32_t *path, int B, int M, int L, int Tl,
+                           int32_t *status, cudaStream_t st) {
+  const int NB = (L + kVB - 1) / kVB;
+  const size_t smem = vit2_smem_bytes(M, L);
+  cudaFuncSetAttribute(dag_viterbi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dag_viterbi_blocked_kernel<<<B, kV2Threads, smem, st>>>(match, links, olen, tlen, lattice, trace, path, M, L, Tl, NB, status);
+  DAGB200_CHECK_LAUNCH("dag_viterbi_blocked_kernel");
+  return 0;
+}
+
+}  // namespace dagb200

@@ -111,6 +111,7 @@ class _DagKernel:
         if EXACT_LOG_DOMAIN is False and match_all.dtype == torch.float32:
             nbytes = int(self.lib.dagb200_dag_loss_workspace_bytes(bsz, tarlen, prelen, translen))
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=match_all.device) if nbytes else None
+        self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(match_all.device):
             rc = self.lib.dagb200_dag_loss(_ptr(match_all), _ptr(links), _ptr(output_length), _ptr(target_length),
                                            _ptr(alpha), _ptr(beta), _DTYPE_CODE[match_all.dtype],
@@ -152,6 +153,7 @@ class _DagKernel:
         nbytes = int(self.lib.dagb200_best_alignment_workspace_bytes(bsz, tarlen, prelen, translen))
         workspace = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
         status = torch.empty(bsz, dtype=torch.int32, device=dev) if _DEBUG else None
+        self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(dev):
             rc = self.lib.dagb200_dag_best_alignment(_ptr(match_all), _ptr(links), _ptr(output_length),
                                                      _ptr(target_length), _ptr(alpha), _ptr(path),

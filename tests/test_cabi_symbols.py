@@ -57,7 +57,7 @@ def test_argument_errors_are_reported_without_touching_the_gpu(lib):
     assert rc == -4
     rc = lib.dagb200_logsoftmax_gather(1, 9, 1, 0, 0, 1, 1, 1, 1, 1, 2, 4, 8, 3, 0, None)
     assert rc == -2
-    assert lib.dagb200_best_alignment_workspace_bytes(2, 4, 8, 7) == 2 * 4 * 8 * 2
+    assert lib.dagb200_best_alignment_workspace_bytes(2, 4, 8, 7) >= 2 * 4 * 8 * 6
     # empty batch is a no-op
     assert lib.dagb200_dag_loss(None, None, None, None, None, None, 0, 0, 4, 8, 7, 1, 1, None, 0, None, None) == 0
     assert lib.dagb200_dag_loss_workspace_bytes(64, 256, 1024, 1023) > 64 * 4 * 1024 * 1024
