@@ -70,6 +70,29 @@ __device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gsrc)
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 struct Dp2Smem {
   float *xbuf;   // [kTpw][32][kPitch] far sums of the tiles of the current batch
   int *fbuf;     // [kTpw][32]         their integer frames
@@ -79,6 +102,8 @@ struct Dp2Smem {
   float *rmax;   // [NB*32]            per-source-vertex transition maximum
   float *stm;    // [NB][32]           chain state carried between chunks: mantissas of the chunk's last row
   int *stf;      // [NB][4]            ... and their group exponents (sweep order)
+  uint4 *tstage; // [kTpw][2][256]     transition tiles in flight (TMA destination, double buffered per tile group)
+  uint64_t *mbar;// [kTpw][2]          their completion barriers
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -209,6 +234,8 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
     sm.stm[x] = 0.f;
   }
   for (int x = threadIdx.x; x < NB * 4; x += kDp2Threads) sm.stf[x] = kNegBig;
+  if (threadIdx.x < kTpw * 2) mbar_init(sm.mbar + threadIdx.x, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int x = threadIdx.x; x < M * NB; x += kDp2Threads) sm.rmtab[x] = kNegBig;
   {
     // rows >= Tn entirely, and columns beyond the last valid block of rows < Tn
@@ -243,6 +270,7 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
   __syncthreads();
 
   // ---- anti-diagonal waves ----------------------------------------------------------------------------
+  uint32_t tuse = 0;   // tiles consumed so far by my tile group (stage = tuse & 1, mbarrier parity = (tuse >> 1) & 1)
   const int nwaves = NBv + NCv - 1;
   for (int w = 0; w < nwaves; w++) {
     const int c_lo = max(0, w - NBv + 1), c_hi = min(NCv - 1, w);
@@ -259,6 +287,8 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
           const int s0 = c * kRows + r0, s1 = c * kRows + r1;
           const bool v0 = s0 < nsteps, v1 = s1 < nsteps;
           const int tp0 = BETA ? Tn - 1 - s0 : s0, tp1 = BETA ? Tn - 1 - s1 : s1;   // previous-row index
+          const bool wd = dbg && !BETA && blockIdx.x == 0 && warp == 0 && lane == 0;
+          long long tw0 = wd ? clock64() : 0;
           // stage this tile's diagonal-block weights and emissions for the chain phase: asynchronous
           // global->shared copies issued now, landed by the end of the MMA loop (2 warps x 16 rows)
           {
@@ -276,41 +306,70 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
             asm volatile("cp.async.commit_group;" ::: "memory");
           }
           const int qlo = max(0, q - band);
+          // far frames of the 32 rows of this tile and the set of source blocks holding any mass: lanes <-> source
+          // blocks (two passes if the band spans more than 32 blocks), one independent smem read + redux per row
+          unsigned long long livemask = 0ull;
           int F0 = kNegBig, F1 = kNegBig;
-          if (v0) for (int qq = qlo; qq < q; qq++) F0 = max(F0, sm.rmtab[tp0 * NB + qq]);
-          if (v1) for (int qq = qlo; qq < q; qq++) F1 = max(F1, sm.rmtab[tp1 * NB + qq]);
+          {
+            int *fbw = sm.fbuf + ts * kRows;
+            const int nsrc = q - qlo;
+            bool any_lo = false, any_hi = false;
+            for (int rr = 0; rr < kRows; rr++) {
+              const int sR = c * kRows + rr;
+              const int tpR = BETA ? Tn - 1 - sR : sR;
+              int v = kNegBig, v2 = kNegBig;
+              if (sR < nsteps) {
+                if (lane < nsrc) v = sm.rmtab[tpR * NB + qlo + lane];
+                if (lane + 32 < nsrc) v2 = sm.rmtab[tpR * NB + qlo + lane + 32];
+              }
+              any_lo = any_lo || v > kNegBig;
+              any_hi = any_hi || v2 > kNegBig;
+              const int fr = __reduce_max_sync(0xffffffffu, max(v, v2));
+              if (rr == r0) F0 = fr;
+              if (rr == r1) F1 = fr;
+              if (sl == 0 && lane == 0) fbw[rr] = fr;
+            }
+            livemask = (unsigned long long)__ballot_sync(0xffffffffu, any_lo) |
+                       ((unsigned long long)__ballot_sync(0xffffffffu, any_hi) << 32);
+          }
           float acc[4][4];
 #pragma unroll
           for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[a][e] = 0.f;
-          const bool live = __any_sync(0xffffffffu, F0 > kNegBig || F1 > kNegBig);
+          const bool live = livemask != 0ull;
+          long long tw1 = wd ? clock64() : 0;
           if (live) {
             const float fs0 = (F0 > kNegBig) ? (float)F0 : 0.f, fs1 = (F1 > kNegBig) ? (float)F1 : 0.f;
             const float *row0 = lat + (int64_t)(v0 ? tp0 : 0) * L, *row1 = lat + (int64_t)(v1 ? tp1 : 0) * L;
-            for (int qq = qlo; qq < q; qq++) {
-              const int Js = BETA ? NBv - 1 - qq : qq;
-              // skip source blocks that are empty on every previous row of this 16-row slice
-              const int m0 = v0 ? sm.rmtab[tp0 * NB + qq] : kNegBig, m1 = v1 ? sm.rmtab[tp1 * NB + qq] : kNegBig;
-              if (!__any_sync(0xffffffffu, m0 > kNegBig || m1 > kNegBig)) continue;
-              const uint4 *tp = tiles + (BETA ? lay.idxB(J, Js) : lay.idxA(Js, J)) * (kTileBytes / 16);
-              uint4 u[8];
+            // previous-row values of one source block for my two rows (columns 2tig, +1, +8, +9 of both k16 steps)
+            auto load_rows = [&](int Js, float (&x)[16]) {
 #pragma unroll
-              for (int k8 = 0; k8 < 8; k8++) u[k8] = __ldg(tp + k8 * 32 + lane);
-              if (qq + 2 < q) {  // pull the tile after next towards L2 while this one is being consumed
-                const int Jn = BETA ? NBv - 1 - (qq + 2) : qq + 2;
-                const uint4 *tn = tiles + (BETA ? lay.idxB(J, Jn) : lay.idxA(Jn, J)) * (kTileBytes / 16);
-                prefetch_l2(tn + lane * 8);
+              for (int ks = 0; ks < 2; ks++) {
+                const int col = kBlk * Js + 16 * ks + 2 * tig;
+                float *y = x + 8 * ks;
+                y[0] = (v0 && col < L) ? row0[col] : ninf;         y[1] = (v0 && col + 1 < L) ? row0[col + 1] : ninf;
+                y[2] = (v1 && col < L) ? row1[col] : ninf;         y[3] = (v1 && col + 1 < L) ? row1[col + 1] : ninf;
+                y[4] = (v0 && col + 8 < L) ? row0[col + 8] : ninf; y[5] = (v0 && col + 9 < L) ? row0[col + 9] : ninf;
+                y[6] = (v1 && col + 8 < L) ? row1[col + 8] : ninf; y[7] = (v1 && col + 9 < L) ? row1[col + 9] : ninf;
               }
+            };
+            auto tile_ptr = [&](int Js) {
+              return tiles + (BETA ? lay.idxB(J, Js) : lay.idxA(Js, J)) * (kTileBytes / 16);
+            };
+            uint4 *stg = sm.tstage + (size_t)ts * 2 * 256;
+            uint64_t *mb = sm.mbar + ts * 2;
+            const bool producer = (sl == 0) && (lane == 0);
+            unsigned long long mk = livemask;
+            // consume one source block: previous-row values in x16 (registers), tile in shared-memory stage
+            auto consume = [&](int Js, const float (&x16)[16], int stage) {
+              const uint4 *tsm = stg + stage * 256;
 #pragma unroll
               for (int ks = 0; ks < 2; ks++) {
                 const int col = kBlk * Js + 16 * ks + 2 * tig;
                 float x[8];
-                // rows r0 / r1, columns col, col+1, col+8, col+9
-                x[0] = (v0 && col < L) ? row0[col] : ninf;         x[1] = (v0 && col + 1 < L) ? row0[col + 1] : ninf;
-                x[2] = (v1 && col < L) ? row1[col] : ninf;         x[3] = (v1 && col + 1 < L) ? row1[col + 1] : ninf;
-                x[4] = (v0 && col + 8 < L) ? row0[col + 8] : ninf; x[5] = (v0 && col + 9 < L) ? row0[col + 9] : ninf;
-                x[6] = (v1 && col + 8 < L) ? row1[col + 8] : ninf; x[7] = (v1 && col + 9 < L) ? row1[col + 9] : ninf;
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = x16[8 * ks + e];
                 if (!BETA) {
                   const float ra = sm.rmax[col], rb = sm.rmax[col + 1], rc = sm.rmax[col + 8], rd = sm.rmax[col + 9];
                   x[0] += ra; x[1] += rb; x[2] += ra; x[3] += rb; x[4] += rc; x[5] += rd; x[6] += rc; x[7] += rd;
@@ -324,18 +383,50 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
                 split_bf16x2(x[2], x[3], ahi[1], alo[1]);
                 split_bf16x2(x[4], x[5], ahi[2], alo[2]);
                 split_bf16x2(x[6], x[7], ahi[3], alo[3]);
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) {
-                  const uint4 &h = u[2 * ks + (nt >> 1)], &l = u[4 + 2 * ks + (nt >> 1)];
-                  const uint32_t bh0 = (nt & 1) ? h.z : h.x, bh1 = (nt & 1) ? h.w : h.y;
-                  const uint32_t bl0 = (nt & 1) ? l.z : l.x, bl1 = (nt & 1) ? l.w : l.y;
-                  mma_bf16_16816(acc[nt], ahi, bh0, bh1);
-                  mma_bf16_16816(acc[nt], alo, bh0, bh1);
-                  mma_bf16_16816(acc[nt], ahi, bl0, bl1);
-                }
+                const uint4 h0 = tsm[(2 * ks) * 32 + lane], h1 = tsm[(2 * ks + 1) * 32 + lane];
+                const uint4 l0 = tsm[(4 + 2 * ks) * 32 + lane], l1 = tsm[(4 + 2 * ks + 1) * 32 + lane];
+                mma_bf16_16816(acc[0], ahi, h0.x, h0.y); mma_bf16_16816(acc[1], ahi, h0.z, h0.w);
+                mma_bf16_16816(acc[2], ahi, h1.x, h1.y); mma_bf16_16816(acc[3], ahi, h1.z, h1.w);
+                mma_bf16_16816(acc[0], alo, h0.x, h0.y); mma_bf16_16816(acc[1], alo, h0.z, h0.w);
+                mma_bf16_16816(acc[2], alo, h1.x, h1.y); mma_bf16_16816(acc[3], alo, h1.z, h1.w);
+                mma_bf16_16816(acc[0], ahi, l0.x, l0.y); mma_bf16_16816(acc[1], ahi, l0.z, l0.w);
+                mma_bf16_16816(acc[2], ahi, l1.x, l1.y); mma_bf16_16816(acc[3], ahi, l1.z, l1.w);
               }
+            };
+            auto next_block = [&]() -> int {   // pops the next live source block (sweep index), -1 when done
+              if (!mk) return -1;
+              const int r = qlo + __ffsll((long long)mk) - 1;
+              mk &= mk - 1;
+              return r;
+            };
+            auto issue = [&](int qn, float (&x16)[16], int stage) {   // TMA the tile, register-load the rows
+              const int Jn = BETA ? NBv - 1 - qn : qn;
+              if (producer) { mbar_expect_tx(mb + stage, kTileBytes); bulk_g2s(stg + stage * 256, tile_ptr(Jn), kTileBytes, mb + stage); }
+              load_rows(Jn, x16);
+            };
+            // software pipeline, unrolled by two so that the two row buffers ping-pong without register copies
+            float xa[16], xb2[16];
+            int qa = next_block(), qb;
+            issue(qa, xa, tuse & 1);
+            while (true) {
+              qb = next_block();
+              if (qb >= 0) issue(qb, xb2, (tuse + 1) & 1);
+              mbar_wait(mb + (tuse & 1), (tuse >> 1) & 1);
+              consume(BETA ? NBv - 1 - qa : qa, xa, tuse & 1);
+              tuse++;
+              group_barrier(1 + ts, 64);   // both warps of the tile are done with the stage before it is refilled
+              if (qb < 0) break;
+              qa = next_block();
+              if (qa >= 0) issue(qa, xa, (tuse + 1) & 1);
+              mbar_wait(mb + (tuse & 1), (tuse >> 1) & 1);
+              consume(BETA ? NBv - 1 - qb : qb, xb2, tuse & 1);
+              tuse++;
+              group_barrier(1 + ts, 64);
+              if (qa < 0) break;
             }
           }
+          long long tw2 = wd ? clock64() : 0;
+          if (wd) { g_dp2_dbg[4] += tw1 - tw0; g_dp2_dbg[5] += tw2 - tw1; g_dp2_dbg[6] += __popcll(livemask); g_dp2_dbg[7] += 1; }
           float *xb = sm.xbuf + (size_t)ts * kRows * kPitch;
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) {
@@ -343,7 +434,6 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
             xb[r0 * kPitch + n] = acc[nt][0]; xb[r0 * kPitch + n + 1] = acc[nt][1];
             xb[r1 * kPitch + n] = acc[nt][2]; xb[r1 * kPitch + n + 1] = acc[nt][3];
           }
-          if (tig == 0) { sm.fbuf[ts * kRows + r0] = F0; sm.fbuf[ts * kRows + r1] = F1; }
           asm volatile("cp.async.wait_all;" ::: "memory");
         }
       }
@@ -434,7 +524,7 @@ dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__
                               const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
                               const unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
                               int32_t *__restrict__ status, int dbg) {
-  extern __shared__ __align__(16) unsigned char dp2_smem[];
+  extern __shared__ __align__(128) unsigned char dp2_smem[];
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
   const int O = (int)olen[b], Tn = (int)tlen[b];
@@ -451,6 +541,8 @@ dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__
   if (status && threadIdx.x == 0 && !is_beta) status[b] = DAGB200_ST_OK;
   Dp2Smem sm;
   float *p = reinterpret_cast<float *>(dp2_smem);
+  sm.tstage = reinterpret_cast<uint4 *>(p);  p += kTpw * 2 * 1024;
+  sm.mbar = reinterpret_cast<uint64_t *>(p); p += kTpw * 2 * 2;
   sm.ut = p;    p += kTpw * kBlk * kBlk;
   sm.xbuf = p;  p += kTpw * kRows * kPitch;
   sm.io = p;    p += kTpw * kRows * kPitch;
@@ -467,7 +559,7 @@ dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__
 
 size_t dp2_smem_bytes(int M, int L) {
   TileLayout lay = TileLayout::make(L);
-  return sizeof(float) * ((size_t)kTpw * kBlk * kBlk + 2 * (size_t)kTpw * kRows * kPitch + (size_t)kTpw * kRows +
+  return sizeof(float) * ((size_t)kTpw * 2 * 1024 + (size_t)kTpw * 4 + (size_t)kTpw * kBlk * kBlk + 2 * (size_t)kTpw * kRows * kPitch + (size_t)kTpw * kRows +
                           2 * (size_t)lay.NB * kBlk + (size_t)lay.NB * 4 + (size_t)M * lay.NB);
 }
 
@@ -475,7 +567,7 @@ int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, in
 
 size_t dp2_workspace_bytes(int B, int L) { return TileLayout::make(L).sample_bytes * (size_t)B; }
 
-bool dp2_supported(int M, int L) { return dp2_smem_bytes(M, L) <= 200 * 1024 && L >= 1; }
+bool dp2_supported(int M, int L) { return dp2_smem_bytes(M, L) <= 226 * 1024 && L >= 1 && (L + kBlk - 1) / kBlk <= 64; }
 
 int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
@@ -494,7 +586,7 @@ int launch_alpha_beta_blocked(const float *match, const float *links, const int6
     long long h[8];
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, g_dp2_dbg, sizeof(h));
-    fprintf(stderr, "[dp2 dbg] cumulative cycles CTA0: alpha gemm %lld chain %lld | beta gemm %lld chain %lld\n", h[0], h[1], h[2], h[3]);
+    fprintf(stderr, "[dp2 dbg] cumulative cycles CTA0: alpha gemm %lld chain %lld | beta gemm %lld chain %lld | warp0: setup %lld loop %lld iters %lld tiles %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
   }
   return 0;
 }
