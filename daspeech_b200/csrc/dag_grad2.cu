@@ -43,7 +43,7 @@ struct G2Planes {            // [level][hi/lo][kG2Kc][kG2Pitch]
   __nv_bfloat16 v[2][2][kG2Kc][kG2Pitch];
 };
 
-__global__ void __launch_bounds__(kG2Threads)
+__global__ void __launch_bounds__(kG2Threads, 2)
 grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ alpha, const float *__restrict__ beta,
                       const float *__restrict__ links, const int64_t *__restrict__ olen,
                       const int64_t *__restrict__ tlen, float *__restrict__ gl, int M, int L, int Tl, int NI) {
@@ -64,15 +64,16 @@ grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ al
   const float ninf = neg_inf_f();
   const bool dead = isinf(Z) || O > L || Tn > M || Tn < 2 || O < 2;
 
-  // carve shared memory: operand staging (aliased by the output tile after the K loop)
-  float *stage_a = reinterpret_cast<float *>(g2_smem);            // [16][128]
-  float *stage_bi = stage_a + kG2Kc * kG2Tile;                    // [16][128]
-  float *stage_bn = stage_bi + kG2Kc * kG2Tile;                   // [16][128]
-  float *u_s = stage_bn + kG2Kc * kG2Tile;                        // [16] (+ padding to 32)
-  float *red_s = u_s + 16;                                        // [16]
-  G2Planes *pa = reinterpret_cast<G2Planes *>(u_s + 32);
+  // carve shared memory: two staging buffers (cp.async, one chunk ahead), frames, operand planes; the output tile
+  // aliases all of it after the K loop
+  constexpr int kStageFloats = 3 * kG2Kc * kG2Tile;             // alpha[t][i-blk], beta[t][i-blk], beta[t+1][n-blk]
+  float *stage_base = reinterpret_cast<float *>(g2_smem);        // [2][3][16][128]
+  float *u_s = stage_base + 2 * kStageFloats;                    // [16]
+  int *lev1_s = reinterpret_cast<int *>(u_s + 16);               // [16] row needs the second exponent level
+  float *red_s = u_s + 32;                                       // [16]
+  G2Planes *pa = reinterpret_cast<G2Planes *>(u_s + 48);
   G2Planes *pb = pa + 1;
-  float *cs = reinterpret_cast<float *>(g2_smem);                 // [128][kG2CPitch] after the loop
+  float *cs = reinterpret_cast<float *>(g2_smem);                // [128][kG2CPitch] after the loop
 
   // ---- tile maximum of the transitions (valid entries only) -------------------------------------------
   bool compute = !dead && i0 < O && n0 < O && (n0 + kG2Tile - 1 > i0);
@@ -107,56 +108,106 @@ grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ al
     const int wi = warp >> 2, wn = warp & 3;     // warp tile: 64 sources x 32 destinations
     const int nsteps = Tn - 1;
     const float shift = emax - Z;
-    for (int t0 = 0; t0 < nsteps; t0 += kG2Kc) {
-      // stage alpha[t][i-block], beta[t][i-block] (liveness) and beta[t+1][n-block], coalesced rows
-      for (int x = tid; x < kG2Kc * kG2Tile; x += kG2Threads) {
-        const int tr = x >> 7, c = x & 127;
-        const int t = t0 + tr;
-        const bool tv = t < nsteps;
-        const int i = i0 + c, n = n0 + c;
-        stage_a[x] = (tv && i < O) ? a[(int64_t)t * L + i] : ninf;
-        stage_bi[x] = (tv && i < O) ? be[(int64_t)t * L + i] : ninf;
-        stage_bn[x] = (tv && n < O) ? be[(int64_t)(t + 1) * L + n] : ninf;
+    const bool vec16 = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(be)) % 16 == 0);
+    // asynchronous staging of one 16-row chunk: alpha[t][i-block], beta[t][i-block] (liveness), beta[t+1][n-block]
+    auto stage_chunk = [&](int t0, int buf) {
+      float *sa = stage_base + buf * kStageFloats, *sbi = sa + kG2Kc * kG2Tile, *sbn = sbi + kG2Kc * kG2Tile;
+      if (vec16) {
+        for (int x = tid; x < kG2Kc * kG2Tile / 4; x += kG2Threads) {
+          const int tr = x >> 5, c = (x & 31) * 4;
+          const int t = t0 + tr;
+          const bool tv = t < nsteps;
+          const int i = i0 + c, n = n0 + c;
+          const uint32_t da = (uint32_t)__cvta_generic_to_shared(sa + tr * kG2Tile + c);
+          const uint32_t db = (uint32_t)__cvta_generic_to_shared(sbi + tr * kG2Tile + c);
+          const uint32_t dn = (uint32_t)__cvta_generic_to_shared(sbn + tr * kG2Tile + c);
+          if (tv && i + 3 < L) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(a + (int64_t)t * L + i) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db), "l"(be + (int64_t)t * L + i) : "memory");
+          } else {
+            *reinterpret_cast<float4 *>(sa + tr * kG2Tile + c) = make_float4(ninf, ninf, ninf, ninf);
+            *reinterpret_cast<float4 *>(sbi + tr * kG2Tile + c) = make_float4(ninf, ninf, ninf, ninf);
+          }
+          if (tv && n + 3 < L)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dn), "l"(be + (int64_t)(t + 1) * L + n) : "memory");
+          else
+            *reinterpret_cast<float4 *>(sbn + tr * kG2Tile + c) = make_float4(ninf, ninf, ninf, ninf);
+        }
+      } else {
+        for (int x = tid; x < kG2Kc * kG2Tile; x += kG2Threads) {
+          const int tr = x >> 7, c = x & 127;
+          const int t = t0 + tr;
+          const bool tv = t < nsteps;
+          const int i = i0 + c, n = n0 + c;
+          sa[x] = (tv && i < L) ? a[(int64_t)t * L + i] : ninf;
+          sbi[x] = (tv && i < L) ? be[(int64_t)t * L + i] : ninf;
+          sbn[x] = (tv && n < L) ? be[(int64_t)(t + 1) * L + n] : ninf;
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_chunk(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < nsteps; t0 += kG2Kc, buf ^= 1) {
+      // next chunk into the other buffer (its last readers passed the barrier after the previous generation)
+      if (t0 + kG2Kc < nsteps) stage_chunk(t0 + kG2Kc, buf ^ 1);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
-      // frame u[t] = max alpha over live vertices of the block (2 rows per warp)
+      const float *stage_a = stage_base + buf * kStageFloats, *stage_bi = stage_a + kG2Kc * kG2Tile,
+                  *stage_bn = stage_bi + kG2Kc * kG2Tile;
+      // frame u[t] = max alpha over live vertices of the block (2 rows per warp); does any live vertex sit more
+      // than one level below it?
 #pragma unroll
       for (int rr = 0; rr < 2; rr++) {
         const int tr = warp * 2 + rr;
-        float m = ninf;
+        float m = ninf, mn = __int_as_float(0x7f800000);
 #pragma unroll
-        for (int c = lane; c < kG2Tile; c += 32)
-          if (stage_bi[tr * kG2Tile + c] > ninf) m = fmaxf(m, stage_a[tr * kG2Tile + c]);
+        for (int c = lane; c < kG2Tile; c += 32) {
+          const int i = i0 + c;
+          if (i < O && stage_bi[tr * kG2Tile + c] > ninf) {
+            const float v = stage_a[tr * kG2Tile + c];
+            m = fmaxf(m, v);
+            if (v > ninf) mn = fminf(mn, v);
+          }
+        }
         m = warp_max(m);
-        if (lane == 0) u_s[tr] = m;
+        mn = -warp_max(-mn);
+        if (lane == 0) { u_s[tr] = m; lev1_s[tr] = (m > ninf && mn < m - kG2Level) ? 1 : 0; }
       }
       __syncthreads();
+      bool need1 = false;
+#pragma unroll
+      for (int tr = 0; tr < kG2Kc; tr++) need1 = need1 || lev1_s[tr] != 0;
       // operand planes: two exponent levels, bf16 hi/lo
       for (int x = tid; x < kG2Kc * kG2Tile; x += kG2Threads) {
         const int tr = x >> 7, c = x & 127;
         const float u = u_s[tr];
         float a0v = 0.f, a1v = 0.f, b0v = 0.f, b1v = 0.f;
         if (u > ninf) {
-          const float xa = (stage_bi[x] > ninf) ? stage_a[x] - u : ninf;
+          const float xa = (i0 + c < O && stage_bi[x] > ninf) ? stage_a[x] - u : ninf;
           if (xa >= -kG2Level) a0v = __expf(xa);
           else if (xa > ninf) a1v = __expf(xa + kG2Level);
-          const float y = stage_bn[x] + u + shift;
+          const float y = (n0 + c < O) ? stage_bn[x] + u + shift : ninf;
           if (y > ninf) {
             b0v = __expf(fminf(y, 80.f));
-            b1v = __expf(fminf(y - kG2Level, 80.f));
+            if (need1) b1v = __expf(fminf(y - kG2Level, 80.f));
           }
         }
-        const __nv_bfloat16 a0h = __float2bfloat16_rn(a0v), a1h = __float2bfloat16_rn(a1v);
-        const __nv_bfloat16 b0h = __float2bfloat16_rn(b0v), b1h = __float2bfloat16_rn(b1v);
+        const __nv_bfloat16 a0h = __float2bfloat16_rn(a0v), b0h = __float2bfloat16_rn(b0v);
         pa->v[0][0][tr][c] = a0h; pa->v[0][1][tr][c] = __float2bfloat16_rn(a0v - __bfloat162float(a0h));
-        pa->v[1][0][tr][c] = a1h; pa->v[1][1][tr][c] = __float2bfloat16_rn(a1v - __bfloat162float(a1h));
         pb->v[0][0][tr][c] = b0h; pb->v[0][1][tr][c] = __float2bfloat16_rn(b0v - __bfloat162float(b0h));
-        pb->v[1][0][tr][c] = b1h; pb->v[1][1][tr][c] = __float2bfloat16_rn(b1v - __bfloat162float(b1h));
+        if (need1) {
+          const __nv_bfloat16 a1h = __float2bfloat16_rn(a1v), b1h = __float2bfloat16_rn(b1v);
+          pa->v[1][0][tr][c] = a1h; pa->v[1][1][tr][c] = __float2bfloat16_rn(a1v - __bfloat162float(a1h));
+          pb->v[1][0][tr][c] = b1h; pb->v[1][1][tr][c] = __float2bfloat16_rn(b1v - __bfloat162float(b1h));
+        }
       }
       __syncthreads();
       // tensor-core contraction over the 16 rows of this chunk (x2 levels, x3 split products)
 #pragma unroll
       for (int lev = 0; lev < 2; lev++) {
+        if (lev == 1 && !need1) break;
         uint32_t bh[4][2], bl[4][2];
 #pragma unroll
         for (int np = 0; np < 2; np++) {
@@ -183,8 +234,9 @@ grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ al
           }
         }
       }
-      __syncthreads();
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
     // stage the output tile (aliases the operand buffers: all warps are past the last barrier)
     const int gid = lane >> 2, tig = lane & 3;
 #pragma unroll
@@ -219,7 +271,7 @@ grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ al
 }
 
 size_t g2_smem_bytes() {
-  const size_t stage = sizeof(float) * (3 * kG2Kc * kG2Tile + 32) + 2 * sizeof(G2Planes);
+  const size_t stage = sizeof(float) * (2 * 3 * kG2Kc * kG2Tile + 48) + 2 * sizeof(G2Planes);
   const size_t cst = sizeof(float) * kG2Tile * kG2CPitch;
   return stage > cst ? stage : cst;
 }
