@@ -292,22 +292,45 @@ def main():
     bwd_ms = sum(fwd_ev[s][1].elapsed_time(bwd_ev[s]) for s in range(K)) / K
     loss_check = float(out[1][:, 0, 0].float().mean().item())
 
-    # dominant kernel: forward = ONE launch (dag_alpha_beta_kernel, alpha and beta chains side by side)
-    if fwd_ms >= bwd_ms:
-        dom = {"kernel": "dag_alpha_beta_kernel<float,1024> (dag_loss forward: alpha+beta, one launch)",
-               "ms": fwd_ms, "bytes": bytes_["fwd"]}
-    else:
-        dom = {"kernel": "dag_loss_backward (grad_match_kernel_v4 + grad_links_kernel, two launches timed together)",
-               "ms": bwd_ms, "bytes": bytes_["bwd"]}
-    ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+    # ---- per-kernel durations: CUDA events recorded by the library on the launch stream around each of its
+    # kernels (dagb200_set_profile), averaged over a few extra steps right after the timed region -----------
+    import ctypes
+    lib = k.lib
+    prof = [0.0] * 5
+    kp = max(3, min(K, 10))
+    lib.dagb200_set_profile(1)
+    buf = (ctypes.c_float * 5)()
+    for _ in range(kp):
+        step()
+        lib.dagb200_get_profile(ctypes.cast(buf, ctypes.c_void_p), 5)
+        for i in range(5):
+            prof[i] += max(buf[i], 0.0) / kp
+    lib.dagb200_set_profile(0)
+    kern = {"dag_prep_kernel": prof[0], "dag_alpha_beta_blocked_kernel": prof[1],
+            "grad_match_kernel_v4": prof[2], "grad_links_mma_kernel": prof[3]}
+    # algorithmic bytes of the launch each kernel belongs to: the forward pair
+    # (precompute + recurrences) moves 4(3N+E), the backward pair 4(4N+2E)
+    N_, E_ = B * M * L, B * L * T
+    kbytes = {"dag_alpha_beta_blocked_kernel": bytes_["fwd"], "grad_links_mma_kernel": 4 * (2 * N_ + 2 * E_),
+              "dag_prep_kernel": 4 * E_, "grad_match_kernel_v4": 4 * 4 * N_}
+    dom_name = max(("dag_alpha_beta_blocked_kernel", "grad_links_mma_kernel"), key=lambda n: kern[n])
+    dom_ms = kern[dom_name] if kern[dom_name] > 0 else max(fwd_ms, bwd_ms)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name)
+    except Exception:
+        pass
+    ach = kbytes[dom_name] / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                "traffic": None, "kernel": dom["kernel"], "kernel_ms": dom["ms"],
-                "algorithmic_bytes_per_launch": dom["bytes"], "peak_source": peak_src,
+                "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms,
+                "algorithmic_bytes_per_launch": kbytes[dom_name], "peak_source": peak_src,
+                "kernels_ms": kern,
                 "step": {"algorithmic_bytes": bytes_["fwd_bwd"], "ms": ms_per_step,
                          "achieved": bytes_["fwd_bwd"] / (ms_per_step * 1e-3) / 1e9,
                          "frac": bytes_["fwd_bwd"] / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
                          "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
-                         "note": "at T=L-1 the recurrences are exp/issue bound, not HBM bound (DESIGN.md)"}}
+                         "note": "HBM roofline of the whole fwd+bwd step; the recurrences are tensor/issue bound "
+                                 "at T=L-1 (DESIGN.md section 5)"}}
 
     # ---- e2e: public autograd API, pinned host inputs, H2D + D2H inside the timed region -------------
     h_match = match.cpu().pin_memory()
@@ -387,7 +410,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, T),
                 "utt_per_sec": B * world / (ms_per_step * 1e-3), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": 3 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
+                "gpu_launches": 4 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, T)
         print(json.dumps(line), flush=True)

@@ -24,6 +24,8 @@ SIGNATURES = {
     "dagb200_last_error": (ctypes.c_char_p, []),
     "dagb200_set_exact": (None, [_int]),
     "dagb200_get_exact": (_int, []),
+    "dagb200_set_profile": (None, [_int]),
+    "dagb200_get_profile": (_int, [_vp, _int]),
     "dagb200_logsoftmax_gather": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                          _int, _int, _int, _int, _int, _vp]),
     "dagb200_logsoftmax_gather_backward": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,

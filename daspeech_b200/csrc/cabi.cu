@@ -32,7 +32,45 @@ int sm_count() {
   return cached;
 }
 
+// ---- optional per-kernel timing: CUDA events recorded on the launch stream around each kernel -------------
+static int g_profile = 0;
+static cudaEvent_t g_ev[kProfMarks];
+static bool g_ev_init = false;
+static bool g_ev_set[kProfMarks];
+
+void prof_mark(int idx, cudaStream_t st) {
+  if (!g_profile || idx < 0 || idx >= kProfMarks) return;
+  if (!g_ev_init) {
+    for (int i = 0; i < kProfMarks; i++) { cudaEventCreate(&g_ev[i]); g_ev_set[i] = false; }
+    g_ev_init = true;
+  }
+  cudaEventRecord(g_ev[idx], st);
+  g_ev_set[idx] = true;
+}
+
 }  // namespace dagb200
+
+extern "C" void dagb200_set_profile(int on) {
+  dagb200::g_profile = on ? 1 : 0;
+  if (dagb200::g_ev_init) for (int i = 0; i < dagb200::kProfMarks; i++) dagb200::g_ev_set[i] = false;
+}
+
+// ms[0] = dag_prep_kernel, ms[1] = blocked alpha/beta kernel (or the log-domain one), ms[2] = grad_match,
+// ms[3] = grad_links, ms[4] = Viterbi kernel of the most recent calls; -1 where nothing was recorded.
+extern "C" int dagb200_get_profile(float *ms, int n) {
+  using namespace dagb200;
+  static const int span[5][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {6, 7}};
+  for (int i = 0; i < n && i < 5; i++) {
+    ms[i] = -1.f;
+    const int a = span[i][0], b = span[i][1];
+    if (g_ev_init && g_ev_set[a] && g_ev_set[b]) {
+      cudaEventSynchronize(g_ev[b]);
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, g_ev[a], g_ev[b]) == cudaSuccess) ms[i] = t;
+    }
+  }
+  return 0;
+}
 
 extern "C" int dagb200_version(void) { return DAGB200_VERSION; }
 extern "C" const char *dagb200_last_error(void) { return dagb200::g_err; }

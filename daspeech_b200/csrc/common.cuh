@@ -99,4 +99,7 @@ int cuda_fail(cudaError_t e, const char *where);
 
 int sm_count();
 
+constexpr int kProfMarks = 8;
+void prof_mark(int idx, cudaStream_t st);   // no-op unless dagb200_set_profile(1)
+
 }  // namespace dagb200

@@ -313,6 +313,7 @@ static int launch_alpha_beta(const T *match, const T *links, const int64_t *olen
                              T *beta, int B, int M, int L, int Tl, bool grad, int32_t *status, cudaStream_t st) {
   const size_t smem = 2 * (size_t)L * sizeof(T);
   dim3 grid(B, grad ? 2 : 1);
+  prof_mark(1, st);
 #define LAUNCH_AB(TH)                                                                                          \
   do {                                                                                                         \
     if (smem > 48 * 1024)                                                                                      \
@@ -324,6 +325,7 @@ static int launch_alpha_beta(const T *match, const T *links, const int64_t *olen
   else LAUNCH_AB(1024);
 #undef LAUNCH_AB
   DAGB200_CHECK_LAUNCH("dag_alpha_beta_kernel");
+  prof_mark(2, st);
   return 0;
 }
 
@@ -332,6 +334,7 @@ static int launch_viterbi(const T *match, const T *links, const int64_t *olen, c
                           uint16_t *trace, int32_t *path, int B, int M, int L, int Tl, int wbits, int32_t *status,
                           cudaStream_t st) {
   const size_t smem = 2 * (size_t)L * sizeof(T);
+  prof_mark(6, st);
 #define LAUNCH_V(TH)                                                                                            \
   do {                                                                                                          \
     if (smem > 48 * 1024)                                                                                       \
@@ -343,6 +346,7 @@ static int launch_viterbi(const T *match, const T *links, const int64_t *olen, c
   else LAUNCH_V(1024);
 #undef LAUNCH_V
   DAGB200_CHECK_LAUNCH("dag_viterbi_kernel");
+  prof_mark(7, st);
   return 0;
 }
 
@@ -364,7 +368,7 @@ static int check_dp_args(const char *who, const void *match, const void *links, 
 using namespace dagb200;
 
 namespace dagb200 {
-size_t dp2_workspace_bytes(int B, int L);
+size_t dp2_workspace_bytes(int B, int M, int L);
 bool dp2_supported(int M, int L);
 extern int g_exact_mode;
 int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
@@ -375,7 +379,7 @@ int launch_alpha_beta_blocked(const float *match, const float *links, const int6
 extern "C" size_t dagb200_dag_loss_workspace_bytes(int B, int M, int L, int T) {
   (void)T;
   if (B <= 0 || M < 1 || L < 1 || !dp2_supported(M, L)) return 0;
-  return dp2_workspace_bytes(B, L);
+  return dp2_workspace_bytes(B, M, L);
 }
 
 extern "C" int dagb200_dag_loss(const void *match, const void *links, const int64_t *output_length,
@@ -395,7 +399,7 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
     cudaError_t e = cudaMemsetAsync(beta, 0, (size_t)B * M * L * esz, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(beta)");
   }
-  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp2_supported(M, L) && workspace_bytes >= dp2_workspace_bytes(B, L))
+  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp2_supported(M, L) && workspace_bytes >= dp2_workspace_bytes(B, M, L))
     return launch_alpha_beta_blocked((const float *)match, (const float *)links, output_length, target_length,
                                      (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
   if (dtype == DAGB200_F32)

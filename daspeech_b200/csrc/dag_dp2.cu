@@ -93,6 +93,19 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Fragment tile of the A operand (32 rows x 32 K, bf16 hi/lo), unit = slice*4 + ks*2 + hl, 32 uint4 per unit:
+// lane (gid, tig) holds a0 = (row gid, k 2tig..+1), a1 = (row gid+8, same k), a2 = (row gid, k+8..+9), a3 = (gid+8, k+8..).
+__device__ __forceinline__ void write_frag_elem(uint4 *tile, int row, int k, float v) {
+  const int slice = row >> 4, r16 = row & 15, ks = k >> 4, k16 = k & 15;
+  const int gid = r16 & 7, reg = (r16 >> 3) | ((k16 >> 3) << 1), tig = (k16 & 7) >> 1, half = k16 & 1;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  __nv_bfloat16 *ph = reinterpret_cast<__nv_bfloat16 *>(tile + (slice * 4 + ks * 2 + 0) * 32 + gid * 4 + tig);
+  __nv_bfloat16 *pl = reinterpret_cast<__nv_bfloat16 *>(tile + (slice * 4 + ks * 2 + 1) * 32 + gid * 4 + tig);
+  ph[reg * 2 + half] = h;
+  pl[reg * 2 + half] = l;
+}
+
 struct Dp2Smem {
   float *xbuf;   // [kTpw][32][kPitch] far sums of the tiles of the current batch
   int *fbuf;     // [kTpw][32]         their integer frames
@@ -170,6 +183,7 @@ __device__ __forceinline__ void chain_column(float (&mant)[kBlk], int (&gexp)[4]
     } else {
       const int shift = fr + e - gexp[G];
       if (shift > 100) {  // the group frame is far too low for this value: re-frame the group (rare)
+        atomicAdd((unsigned long long *)&g_dp2_dbg[BETA ? 7 : 6], 1ull);
 #pragma unroll
         for (int c = G * 8; c < CJ; c++) mant[c] *= pow2i(-shift);
         gexp[G] += shift;
@@ -214,7 +228,7 @@ __device__ __forceinline__ void chain_group(float (&mant)[kBlk], int (&gexp)[4],
 
 // One direction of one utterance.
 template <bool BETA>
-__device__ void blocked_chain(const float *__restrict__ match, float *__restrict__ lat, const unsigned char *__restrict__ ws,
+__device__ void blocked_chain(const float *__restrict__ match, float *__restrict__ lat, unsigned char *__restrict__ ws,
                               const TileLayout &lay, const Dp2Smem &sm, int O, int Tn, int M, int L, int Tl, bool dbg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
@@ -227,6 +241,7 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
   const float *g_rmax = reinterpret_cast<const float *>(ws + lay.off_rmax);
   const float *diag = reinterpret_cast<const float *>(ws + (BETA ? lay.off_diagB : lay.off_diagA));
   const uint4 *tiles = reinterpret_cast<const uint4 *>(ws + (BETA ? lay.off_tilesB : lay.off_tilesA));
+  uint4 *afrag = reinterpret_cast<uint4 *>(ws + (BETA ? lay.off_afragB : lay.off_afragA));   // [chunk][q] 256 uint4
 
   // ---- prologue: -inf padding, the seed row, per-vertex maxima, frame table, chain state ------------------
   for (int x = threadIdx.x; x < NB * kBlk; x += kDp2Threads) {
@@ -234,6 +249,7 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
     sm.stm[x] = 0.f;
   }
   for (int x = threadIdx.x; x < NB * 4; x += kDp2Threads) sm.stf[x] = kNegBig;
+  for (int x = threadIdx.x; x < NBv * 256; x += kDp2Threads) afrag[x] = make_uint4(0u, 0u, 0u, 0u);   // chunk 0
   if (threadIdx.x < kTpw * 2) mbar_init(sm.mbar + threadIdx.x, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int x = threadIdx.x; x < M * NB; x += kDp2Threads) sm.rmtab[x] = kNegBig;
@@ -262,9 +278,12 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
     const float v2 = v * kLog2e;
     if (v2 > -1.0e30f) {
       const int F = (int)ceilf(v2);
-      sm.stm[q * kBlk + ci] = exp2f(v2 - (float)F);  // in (0.5, 1]
+      const float mant0 = exp2f(v2 - (float)F);  // in (0.5, 1]
+      sm.stm[q * kBlk + ci] = mant0;
       sm.stf[q * 4 + (ci >> 3)] = F;
       sm.rmtab[seed_row * NB + q] = F + 1;
+      // row 0 of the chunk-0 fragment tile of block q: value mant0/2 in frame F+1, at K index = vertex offset jj
+      write_frag_elem(afrag + (size_t)q * 256, 0, jj, 0.5f * mant0);
     }
   }
   __syncthreads();
@@ -340,19 +359,11 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
           const bool live = livemask != 0ull;
           long long tw1 = wd ? clock64() : 0;
           if (live) {
-            const float fs0 = (F0 > kNegBig) ? (float)F0 : 0.f, fs1 = (F1 > kNegBig) ? (float)F1 : 0.f;
-            const float *row0 = lat + (int64_t)(v0 ? tp0 : 0) * L, *row1 = lat + (int64_t)(v1 ? tp1 : 0) * L;
-            // previous-row values of one source block for my two rows (columns 2tig, +1, +8, +9 of both k16 steps)
-            auto load_rows = [&](int Js, float (&x)[16]) {
-#pragma unroll
-              for (int ks = 0; ks < 2; ks++) {
-                const int col = kBlk * Js + 16 * ks + 2 * tig;
-                float *y = x + 8 * ks;
-                y[0] = (v0 && col < L) ? row0[col] : ninf;         y[1] = (v0 && col + 1 < L) ? row0[col + 1] : ninf;
-                y[2] = (v1 && col < L) ? row1[col] : ninf;         y[3] = (v1 && col + 1 < L) ? row1[col + 1] : ninf;
-                y[4] = (v0 && col + 8 < L) ? row0[col + 8] : ninf; y[5] = (v0 && col + 9 < L) ? row0[col + 9] : ninf;
-                y[6] = (v1 && col + 8 < L) ? row1[col + 8] : ninf; y[7] = (v1 && col + 9 < L) ? row1[col + 9] : ninf;
-              }
+            // A operand of one source block for my 16-row slice: cached fragments (hi ks0, lo ks0, hi ks1, lo ks1),
+            // written by the chain warp that produced those rows; plain loads (same CTA, ordered by the barriers)
+            auto load_frag = [&](int qn, uint4 (&f)[4]) {
+              const uint4 *ft = afrag + ((size_t)c * NBv + qn) * 256 + (sl * 4) * 32 + lane;
+              f[0] = ft[0]; f[1] = ft[32]; f[2] = ft[64]; f[3] = ft[96];
             };
             auto tile_ptr = [&](int Js) {
               return tiles + (BETA ? lay.idxB(J, Js) : lay.idxA(Js, J)) * (kTileBytes / 16);
@@ -361,28 +372,23 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
             uint64_t *mb = sm.mbar + ts * 2;
             const bool producer = (sl == 0) && (lane == 0);
             unsigned long long mk = livemask;
-            // consume one source block: previous-row values in x16 (registers), tile in shared-memory stage
-            auto consume = [&](int Js, const float (&x16)[16], int stage) {
+            // consume one source block: rescale the cached fragments from the source rows' frames to this tile's far
+            // frames (exact powers of two), then 3 split products per n-tile against the staged transition tile
+            auto consume = [&](int qs, const uint4 (&f)[4], int stage) {
               const uint4 *tsm = stg + stage * 256;
+              const int Fs0 = v0 ? sm.rmtab[tp0 * NB + qs] : kNegBig, Fs1 = v1 ? sm.rmtab[tp1 * NB + qs] : kNegBig;
+              const float s0 = (Fs0 > kNegBig) ? pow2i(Fs0 - F0) : 0.f, s1 = (Fs1 > kNegBig) ? pow2i(Fs1 - F1) : 0.f;
+              const __nv_bfloat162 sc0 = __floats2bfloat162_rn(s0, s0), sc1 = __floats2bfloat162_rn(s1, s1);
+              auto scale = [&](uint32_t v, const __nv_bfloat162 &sc) -> uint32_t {
+                __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162 *>(&v), sc);
+                return *reinterpret_cast<uint32_t *>(&r);
+              };
 #pragma unroll
               for (int ks = 0; ks < 2; ks++) {
-                const int col = kBlk * Js + 16 * ks + 2 * tig;
-                float x[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) x[e] = x16[8 * ks + e];
-                if (!BETA) {
-                  const float ra = sm.rmax[col], rb = sm.rmax[col + 1], rc = sm.rmax[col + 8], rd = sm.rmax[col + 9];
-                  x[0] += ra; x[1] += rb; x[2] += ra; x[3] += rb; x[4] += rc; x[5] += rd; x[6] += rc; x[7] += rd;
-                }
-                x[0] = exp2f(fmaf(x[0], kLog2e, -fs0)); x[1] = exp2f(fmaf(x[1], kLog2e, -fs0));
-                x[2] = exp2f(fmaf(x[2], kLog2e, -fs1)); x[3] = exp2f(fmaf(x[3], kLog2e, -fs1));
-                x[4] = exp2f(fmaf(x[4], kLog2e, -fs0)); x[5] = exp2f(fmaf(x[5], kLog2e, -fs0));
-                x[6] = exp2f(fmaf(x[6], kLog2e, -fs1)); x[7] = exp2f(fmaf(x[7], kLog2e, -fs1));
+                const uint4 fh = f[2 * ks], fl = f[2 * ks + 1];
                 uint32_t ahi[4], alo[4];
-                split_bf16x2(x[0], x[1], ahi[0], alo[0]);
-                split_bf16x2(x[2], x[3], ahi[1], alo[1]);
-                split_bf16x2(x[4], x[5], ahi[2], alo[2]);
-                split_bf16x2(x[6], x[7], ahi[3], alo[3]);
+                ahi[0] = scale(fh.x, sc0); ahi[1] = scale(fh.y, sc1); ahi[2] = scale(fh.z, sc0); ahi[3] = scale(fh.w, sc1);
+                alo[0] = scale(fl.x, sc0); alo[1] = scale(fl.y, sc1); alo[2] = scale(fl.z, sc0); alo[3] = scale(fl.w, sc1);
                 const uint4 h0 = tsm[(2 * ks) * 32 + lane], h1 = tsm[(2 * ks + 1) * 32 + lane];
                 const uint4 l0 = tsm[(4 + 2 * ks) * 32 + lane], l1 = tsm[(4 + 2 * ks + 1) * 32 + lane];
                 mma_bf16_16816(acc[0], ahi, h0.x, h0.y); mma_bf16_16816(acc[1], ahi, h0.z, h0.w);
@@ -399,34 +405,34 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
               mk &= mk - 1;
               return r;
             };
-            auto issue = [&](int qn, float (&x16)[16], int stage) {   // TMA the tile, register-load the rows
+            auto issue = [&](int qn, uint4 (&f)[4], int stage) {   // TMA the tile, register-load the fragments
               const int Jn = BETA ? NBv - 1 - qn : qn;
               if (producer) { mbar_expect_tx(mb + stage, kTileBytes); bulk_g2s(stg + stage * 256, tile_ptr(Jn), kTileBytes, mb + stage); }
-              load_rows(Jn, x16);
+              load_frag(qn, f);
             };
-            // software pipeline, unrolled by two so that the two row buffers ping-pong without register copies
-            float xa[16], xb2[16];
+            // software pipeline, unrolled by two so that the two fragment buffers ping-pong without register copies
+            uint4 fa[4], fb4[4];
             int qa = next_block(), qb;
-            issue(qa, xa, tuse & 1);
+            issue(qa, fa, tuse & 1);
             while (true) {
               qb = next_block();
-              if (qb >= 0) issue(qb, xb2, (tuse + 1) & 1);
+              if (qb >= 0) issue(qb, fb4, (tuse + 1) & 1);
               mbar_wait(mb + (tuse & 1), (tuse >> 1) & 1);
-              consume(BETA ? NBv - 1 - qa : qa, xa, tuse & 1);
+              consume(qa, fa, tuse & 1);
               tuse++;
               group_barrier(1 + ts, 64);   // both warps of the tile are done with the stage before it is refilled
               if (qb < 0) break;
               qa = next_block();
-              if (qa >= 0) issue(qa, xa, (tuse + 1) & 1);
+              if (qa >= 0) issue(qa, fa, (tuse + 1) & 1);
               mbar_wait(mb + (tuse & 1), (tuse >> 1) & 1);
-              consume(BETA ? NBv - 1 - qb : qb, xb2, tuse & 1);
+              consume(qb, fb4, tuse & 1);
               tuse++;
               group_barrier(1 + ts, 64);
               if (qa < 0) break;
             }
           }
           long long tw2 = wd ? clock64() : 0;
-          if (wd) { g_dp2_dbg[4] += tw1 - tw0; g_dp2_dbg[5] += tw2 - tw1; g_dp2_dbg[6] += __popcll(livemask); g_dp2_dbg[7] += 1; }
+          if (wd) { g_dp2_dbg[4] += tw1 - tw0; g_dp2_dbg[5] += tw2 - tw1; }
           float *xb = sm.xbuf + (size_t)ts * kRows * kPitch;
 #pragma unroll
           for (int nt = 0; nt < 4; nt++) {
@@ -496,6 +502,61 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
 #pragma unroll
             for (int g = 0; g < 4; g++) sm.stf[q * 4 + g] = gexp[g];
           }
+          // publish my row as A-operand for the tiles that will consume it as a previous row: normalised by the
+          // row frame (value < 1), through shared memory into fragment order.  Producer step s feeds consumer row
+          // (s + 1): rows 1..31 of this chunk's fragment tile, and row 0 of the next chunk's.
+          {
+            float *vt = const_cast<float *>(sm.xbuf + (size_t)ts * kRows * kPitch);   // far sums are consumed: reuse
+#pragma unroll
+            for (int ci = 0; ci < kBlk; ci++) {
+              const int k = BETA ? (kBlk - 1 - ci) : ci;                               // K index = vertex offset
+              vt[lane * kPitch + k] = (maxe > kNegBig) ? mant[ci] * pow2i(gexp[ci >> 3] - maxe) : 0.f;
+            }
+            __syncwarp();
+            uint4 *ft = afrag + ((size_t)c * NBv + q) * 256;
+            const int fgid = lane >> 2, ftig = lane & 3;
+#pragma unroll
+            for (int slice = 0; slice < 2; slice++)
+#pragma unroll
+              for (int ks = 0; ks < 2; ks++) {
+                // consumer rows rho = 16*slice + {fgid, fgid+8}  <- producer rows rho-1
+                const int rA = 16 * slice + fgid - 1, rB = rA + 8;
+                const int k0 = 16 * ks + 2 * ftig;
+                float e[8];
+                e[0] = rA >= 0 ? vt[rA * kPitch + k0] : 0.f;     e[1] = rA >= 0 ? vt[rA * kPitch + k0 + 1] : 0.f;
+                e[2] = vt[rB * kPitch + k0];                      e[3] = vt[rB * kPitch + k0 + 1];
+                e[4] = rA >= 0 ? vt[rA * kPitch + k0 + 8] : 0.f; e[5] = rA >= 0 ? vt[rA * kPitch + k0 + 9] : 0.f;
+                e[6] = vt[rB * kPitch + k0 + 8];                  e[7] = vt[rB * kPitch + k0 + 9];
+                uint4 hi, lo;
+                split_bf16x2(e[0], e[1], hi.x, lo.x);
+                split_bf16x2(e[2], e[3], hi.y, lo.y);
+                split_bf16x2(e[4], e[5], hi.z, lo.z);
+                split_bf16x2(e[6], e[7], hi.w, lo.w);
+                if (slice == 0 && fgid == 0) {
+                  // row 0 of this tile belongs to the previous chunk's producer (or the seed): keep a0 / a2
+                  uint32_t *ph = reinterpret_cast<uint32_t *>(ft + (slice * 4 + ks * 2 + 0) * 32 + lane);
+                  uint32_t *pl = reinterpret_cast<uint32_t *>(ft + (slice * 4 + ks * 2 + 1) * 32 + lane);
+                  ph[1] = hi.y; ph[3] = hi.w; pl[1] = lo.y; pl[3] = lo.w;
+                } else {
+                  ft[(slice * 4 + ks * 2 + 0) * 32 + lane] = hi;
+                  ft[(slice * 4 + ks * 2 + 1) * 32 + lane] = lo;
+                }
+              }
+            // my chunk's last row is row 0 of the next chunk's tile
+            if (c + 1 < NCv && lane < 4) {
+              uint4 *fn = afrag + ((size_t)(c + 1) * NBv + q) * 256;
+#pragma unroll
+              for (int ks = 0; ks < 2; ks++) {
+                const int k0 = 16 * ks + 2 * lane;   // lane = tig of (gid 0)
+                uint32_t h0, l0, h2, l2;
+                split_bf16x2(vt[31 * kPitch + k0], vt[31 * kPitch + k0 + 1], h0, l0);
+                split_bf16x2(vt[31 * kPitch + k0 + 8], vt[31 * kPitch + k0 + 9], h2, l2);
+                uint32_t *ph = reinterpret_cast<uint32_t *>(fn + (ks * 2 + 0) * 32 + lane);
+                uint32_t *pl = reinterpret_cast<uint32_t *>(fn + (ks * 2 + 1) * 32 + lane);
+                ph[0] = h0; ph[2] = h2; pl[0] = l0; pl[2] = l2;
+              }
+            }
+          }
           __syncwarp();
           // lattice values: coalesced row writes (lane = column)
           const float *iot = sm.io + (size_t)ts * kRows * kPitch;
@@ -522,7 +583,7 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
 __global__ void __launch_bounds__(kDp2Threads, 1)
 dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__restrict__ olen,
                               const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
-                              const unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
+                              unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
                               int32_t *__restrict__ status, int dbg) {
   extern __shared__ __align__(128) unsigned char dp2_smem[];
   const int b = blockIdx.x;
@@ -552,41 +613,44 @@ dag_alpha_beta_blocked_kernel(const float *__restrict__ match, const int64_t *__
   sm.stf = reinterpret_cast<int *>(p);  p += lay.NB * 4;
   sm.rmtab = reinterpret_cast<int *>(p);
   const float *m = match + b * latsz;
-  const unsigned char *wsb = ws + (size_t)b * lay.sample_bytes;
+  unsigned char *wsb = ws + (size_t)b * lay.sample_bytes;
   if (is_beta) blocked_chain<true>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg != 0);
   else blocked_chain<false>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg != 0);
 }
 
 size_t dp2_smem_bytes(int M, int L) {
-  TileLayout lay = TileLayout::make(L);
+  TileLayout lay = TileLayout::make(L, M);
   return sizeof(float) * ((size_t)kTpw * 2 * 1024 + (size_t)kTpw * 4 + (size_t)kTpw * kBlk * kBlk + 2 * (size_t)kTpw * kRows * kPitch + (size_t)kTpw * kRows +
                           2 * (size_t)lay.NB * kBlk + (size_t)lay.NB * 4 + (size_t)M * lay.NB);
 }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int L, int Tl, cudaStream_t st);
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, cudaStream_t st);
 
-size_t dp2_workspace_bytes(int B, int L) { return TileLayout::make(L).sample_bytes * (size_t)B; }
+size_t dp2_workspace_bytes(int B, int M, int L) { return TileLayout::make(L, M).sample_bytes * (size_t)B; }
 
 bool dp2_supported(int M, int L) { return dp2_smem_bytes(M, L) <= 226 * 1024 && L >= 1 && (L + kBlk - 1) / kBlk <= 64; }
 
 int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
                               int32_t *status, cudaStream_t st) {
-  int rc = launch_dag_prep(links, olen, workspace, B, L, Tl, st);
+  prof_mark(0, st);
+  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, st);
   if (rc) return rc;
-  TileLayout lay = TileLayout::make(L);
+  prof_mark(1, st);
+  TileLayout lay = TileLayout::make(L, M);
   dim3 grid(B, grad ? 2 : 1);
   const size_t smem = dp2_smem_bytes(M, L);
   static const bool dbg = getenv("DAGB200_DP2_DEBUG") != nullptr;
   cudaFuncSetAttribute(dag_alpha_beta_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dag_alpha_beta_blocked_kernel<<<grid, kDp2Threads, smem, st>>>(match, olen, tlen, alpha, beta,
-                                                                (const unsigned char *)workspace, M, L, Tl, lay, status, dbg ? 1 : 0);
+                                                                (unsigned char *)workspace, M, L, Tl, lay, status, dbg ? 1 : 0);
   DAGB200_CHECK_LAUNCH("dag_alpha_beta_blocked_kernel");
+  prof_mark(2, st);
   if (dbg) {
     long long h[8];
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, g_dp2_dbg, sizeof(h));
-    fprintf(stderr, "[dp2 dbg] cumulative cycles CTA0: alpha gemm %lld chain %lld | beta gemm %lld chain %lld | warp0: setup %lld loop %lld iters %lld tiles %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    fprintf(stderr, "[dp2 dbg] cumulative cycles CTA0: alpha gemm %lld chain %lld | beta gemm %lld chain %lld | warp0: setup %lld loop %lld | reframes alpha %lld beta %lld\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
   }
   return 0;
 }

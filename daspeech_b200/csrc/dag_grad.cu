@@ -141,6 +141,7 @@ extern "C" int dagb200_dag_loss_backward(const void *grad_output, const void *al
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t lat = (int64_t)M * L, total = lat * B;
   const int blocks = sm_count() * 8;
+  prof_mark(3, st);
   if (dtype == DAGB200_F32) {
     const bool v4 = (lat % 4 == 0) && (((uintptr_t)alpha | (uintptr_t)beta | (uintptr_t)match | (uintptr_t)grad_match) & 15) == 0;
     if (v4)
@@ -150,6 +151,7 @@ extern "C" int dagb200_dag_loss_backward(const void *grad_output, const void *al
       grad_match_kernel<float><<<blocks, 256, 0, st>>>((const float *)grad_output, (const float *)alpha, (const float *)beta,
                                                       (const float *)match, (float *)grad_match, lat, total);
     DAGB200_CHECK_LAUNCH("grad_match_kernel");
+    prof_mark(4, st);
     if (!g_exact_mode) {
       int rc = launch_grad_links_mma((const float *)grad_output, (const float *)alpha, (const float *)beta,
                                      (const float *)links, output_length, target_length, (float *)grad_links, B, M, L, T, st);
@@ -163,6 +165,7 @@ extern "C" int dagb200_dag_loss_backward(const void *grad_output, const void *al
                                                               (const float *)links, output_length, target_length, (float *)grad_links, M, L, T);
       DAGB200_CHECK_LAUNCH("grad_links_kernel");
     }
+    prof_mark(5, st);
   } else {
     grad_match_kernel<double><<<blocks, 256, 0, st>>>((const double *)grad_output, (const double *)alpha, (const double *)beta,
                                                      (const double *)match, (double *)grad_match, lat, total);

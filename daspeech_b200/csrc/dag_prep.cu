@@ -99,8 +99,8 @@ dag_prep_kernel(const float *__restrict__ links, const int64_t *__restrict__ ole
   }
 }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int L, int Tl, cudaStream_t st) {
-  TileLayout lay = TileLayout::make(L);
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, cudaStream_t st) {
+  TileLayout lay = TileLayout::make(L, M);
   dim3 grid(lay.NB, B);
   dag_prep_kernel<<<grid, 256, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay);
   DAGB200_CHECK_LAUNCH("dag_prep_kernel");

@@ -8,6 +8,10 @@
 //   tilesA[NB(NB-1)/2] 4 KB  off-diagonal tile (I<J) as the B operand of mma.m16n8k16 with K = source vertex,
 //                            N = destination vertex, bf16 hi plane then bf16 lo plane, in FRAGMENT order
 //   tilesB[NB(NB-1)/2] 4 KB  the same tile as the B operand with K = destination vertex, N = source vertex
+//   afragA/afragB [NC][NB] 4 KB  written by the recurrences themselves: the previous-row masses of (chunk, block)
+//                            as the A operand (rows = the chunk's 32 previous rows, K = vertex), normalised per row
+//                            by the integer frame of the frame table, bf16 hi/lo, fragment order:
+//                            unit = slice*4 + ks*2 + hl (slice = 16-row half), .x.y.z.w = a0..a3 of mma.m16n8k16
 // with P'[i][j] = exp(links[i][j-i-1] - rmax[i])  (0 outside the band / beyond the graph).
 //
 // Fragment order of one 32(K) x 32(N) operand tile Bop[k][n]: eight uint4 "units" q, unit q is stored as 32
@@ -27,10 +31,13 @@ constexpr int kTileBytes = 4096;    // one off-diagonal operand tile (hi + lo pl
 
 struct TileLayout {
   int NB;                // blocks per utterance
-  size_t off_rmax, off_diagA, off_diagB, off_tilesA, off_tilesB, sample_bytes;
-  __host__ __device__ static inline TileLayout make(int L) {
+  int NC;                // 32-row chunks per utterance
+  size_t off_rmax, off_diagA, off_diagB, off_tilesA, off_tilesB, off_afragA, off_afragB, sample_bytes;
+  __host__ __device__ static inline TileLayout make(int L, int M = 2) {
     TileLayout t;
     t.NB = (L + kBlk - 1) / kBlk;
+    t.NC = (M - 1 + kBlk - 1) / kBlk;
+    if (t.NC < 1) t.NC = 1;
     const size_t ntri = (size_t)t.NB * (t.NB - 1) / 2;
     size_t o = 0;
     t.off_rmax = o;   o += (size_t)t.NB * kBlk * sizeof(float);
@@ -38,6 +45,9 @@ struct TileLayout {
     t.off_diagB = o;  o += (size_t)t.NB * kBlk * kBlk * sizeof(float);
     t.off_tilesA = o; o += ntri * kTileBytes;
     t.off_tilesB = o; o += ntri * kTileBytes;
+    // A-operand fragment cache of the recurrences: [chunk][block in sweep order] 4 KB each, per direction
+    t.off_afragA = o; o += (size_t)t.NC * t.NB * kTileBytes;
+    t.off_afragB = o; o += (size_t)t.NC * t.NB * kTileBytes;
     t.sample_bytes = (o + 255) & ~(size_t)255;
     return t;
   }

@@ -356,8 +356,10 @@ int launch_viterbi_blocked(const float *match, const float *links, const int64_t
   const int NB = (L + kVB - 1) / kVB;
   const size_t smem = vit2_smem_bytes(M, L);
   cudaFuncSetAttribute(dag_viterbi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  prof_mark(6, st);
   dag_viterbi_blocked_kernel<<<B, kV2Threads, smem, st>>>(match, links, olen, tlen, lattice, trace, path, M, L, Tl, NB, status);
   DAGB200_CHECK_LAUNCH("dag_viterbi_blocked_kernel");
+  prof_mark(7, st);
   return 0;
 }
 

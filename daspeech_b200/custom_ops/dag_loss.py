@@ -76,6 +76,23 @@ class _DagKernel:
         if not torch.cuda.is_available():
             raise RuntimeError("You need GPU to use the custom cuda operations")
         self.lib = _lib.load()
+        self._scratch = {}
+
+    def _workspace(self, nbytes, device):
+        """Per-(device, stream) scratch for the blocked kernels, grown on demand and kept across calls: the
+        contents only live for the duration of one call, and calls on a stream are ordered.  (Allocating ~400 MB
+        per call makes the caching allocator fall back to synchronous cudaMalloc when it alternates with the
+        268 MB gradient buffers.)"""
+        if nbytes <= 0:
+            return None
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._scratch.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = None
+            self._scratch.pop(key, None)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._scratch[key] = buf
+        return buf
 
     # ---- shared argument checks (dag_loss.cu:317-332 / dag_best_alignment.cu:212-227) -------------------
     @staticmethod
@@ -110,7 +127,7 @@ class _DagKernel:
         nbytes = 0
         if EXACT_LOG_DOMAIN is False and match_all.dtype == torch.float32:
             nbytes = int(self.lib.dagb200_dag_loss_workspace_bytes(bsz, tarlen, prelen, translen))
-        workspace = torch.empty(nbytes, dtype=torch.uint8, device=match_all.device) if nbytes else None
+        workspace = self._workspace(nbytes, match_all.device)
         self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(match_all.device):
             rc = self.lib.dagb200_dag_loss(_ptr(match_all), _ptr(links), _ptr(output_length), _ptr(target_length),
@@ -151,7 +168,7 @@ class _DagKernel:
         alpha = torch.empty((bsz, tarlen, prelen), dtype=match_all.dtype, device=dev) if want_alpha else None
         path = torch.empty((bsz, prelen), dtype=torch.int32, device=dev)
         nbytes = int(self.lib.dagb200_best_alignment_workspace_bytes(bsz, tarlen, prelen, translen))
-        workspace = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        workspace = self._workspace(max(nbytes, 1), dev)
         status = torch.empty(bsz, dtype=torch.int32, device=dev) if _DEBUG else None
         self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(dev):

@@ -61,6 +61,13 @@ const char *dagb200_last_error(void);
 void dagb200_set_exact(int on);
 int dagb200_get_exact(void);
 
+/* Measurement aid (off by default): with dagb200_set_profile(1) every entry point records CUDA events on its
+ * stream around each kernel it launches; dagb200_get_profile() synchronises on them and returns the durations of
+ * the most recent launches in ms: [0] transition-tile precompute, [1] alpha/beta recurrences, [2] grad_match,
+ * [3] grad_links, [4] Viterbi; -1 where nothing was recorded.                                              */
+void dagb200_set_profile(int on);
+int dagb200_get_profile(float *ms, int n);
+
 /* Replaces `logsoftmax_gather` (dag_loss.cpp:22, logsoftmax_gather.cu:313-377).
  *   logits  [B][L][V] contiguous, dtype F32/F16/BF16/F64; OVERWRITTEN with softmax probabilities
  *           iff require_gradient != 0 (the reference's in-place contract, dag_loss.py:272-274)
