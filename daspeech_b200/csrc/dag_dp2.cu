@@ -114,49 +114,61 @@ struct Dp2Smem {
   int *rmtab;    // [M][NB]            per (row, block q) integer upper bound of log2(outgoing mass)
   float *rmax;   // [NB*32]            per-source-vertex transition maximum
   float *stm;    // [NB][32]           chain state carried between chunks: mantissas of the chunk's last row
-  int *stf;      // [NB][4]            ... and their group exponents (sweep order)
+  int *stf;      // [NB]               ... and their common frame
   uint4 *tstage; // [kTpw][2][256]     transition tiles in flight (TMA destination, double buffered per tile group)
   uint64_t *mbar;// [kTpw][2]          their completion barriers
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// One column of the diagonal-block sweep.  CJ is a compile-time constant so that mant[] stays in registers.
-template <bool BETA, int CJ>
-__device__ __forceinline__ void chain_column(float (&mant)[kBlk], int (&gexp)[4], int &maxe, const float *utw,
-                                             float *iow, const float *xbw, int lane, int FI, float d0m, int d0f,
+// Diagonal-block sweep, lanes = rows.  The 32 columns are processed in four groups of 8 (runtime loop, so the
+// code stays small enough for the instruction cache); the mantissas of the current group live in registers,
+// those of the completed groups in my row of the far-sum tile (shared memory: a cell's slot holds its far sum
+// until the cell is computed, its mantissa afterwards) under ONE common frame CF.
+struct ChainRow {
+  int CF;      // frame of the completed groups (kNegBig: nothing yet)
+  int maxe;    // integer upper bound of log2(outgoing mass) over my row
+};
+
+// K = column inside the group (compile time), G = group (runtime)
+template <bool BETA, int K>
+__device__ __forceinline__ void chain_column(float (&cur)[8], int &gexpG, ChainRow &st, int G, const float *utw,
+                                             float *mrow, float *iow, int lane, int FI, float d0m, int d0f,
                                              const float (&ew)[8], const float (&mm)[8], int KE, bool rowvalid,
                                              int jbase, int t, int O, const float *rmax_blk) {
-  constexpr int G = CJ >> 3;
-  // (1) predecessor sum of MY row for the next row's column CJ: sum_{ci < CJ} mant[ci] * U[ci][CJ]
-  float dm = 0.f;
-  int df = kNegBig;
-  if (CJ > 0) {
-    float ps[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c4 = 0; c4 < CJ; c4 += 4) {
-      const float4 u4 = *reinterpret_cast<const float4 *>(utw + CJ * kBlk + c4);  // broadcast
-      float s = ps[c4 >> 3];
-      s = fmaf(mant[c4], u4.x, s);
-      if (c4 + 1 < CJ) s = fmaf(mant[c4 + 1], u4.y, s);
-      if (c4 + 2 < CJ) s = fmaf(mant[c4 + 2], u4.z, s);
-      if (c4 + 3 < CJ) s = fmaf(mant[c4 + 3], u4.w, s);
-      ps[c4 >> 3] = s;
-    }
-    constexpr int GL = (CJ > 0 ? CJ - 1 : 0) >> 3;  // last group that has a column < CJ
-#pragma unroll
-    for (int g = 0; g <= GL; g++) df = max(df, gexp[g]);
-#pragma unroll
-    for (int g = 0; g <= GL; g++) dm = fmaf(ps[g], pow2i(gexp[g] - df), dm);
+  const int cj = 8 * G + K;
+  const float *urow = utw + cj * kBlk;                 // U[ci][cj] for ci = 0..31 (0 for ci >= cj)
+  // (1) predecessor sum of MY row for the next row's column cj
+  float pdone = 0.f;                                   // completed groups, frame st.CF
+  for (int g = 0; g < G; g++) {
+    const float4 u0 = *reinterpret_cast<const float4 *>(urow + 8 * g);
+    const float4 u1 = *reinterpret_cast<const float4 *>(urow + 8 * g + 4);
+    // slot of sweep column ci in my row: its vertex offset (alpha: ci, beta: 31 - ci)
+    const float *mr = BETA ? mrow + (kBlk - 1 - 8 * g) : mrow + 8 * g;
+    constexpr int D = BETA ? -1 : 1;
+    pdone = fmaf(mr[0 * D], u0.x, pdone); pdone = fmaf(mr[1 * D], u0.y, pdone);
+    pdone = fmaf(mr[2 * D], u0.z, pdone); pdone = fmaf(mr[3 * D], u0.w, pdone);
+    pdone = fmaf(mr[4 * D], u1.x, pdone); pdone = fmaf(mr[5 * D], u1.y, pdone);
+    pdone = fmaf(mr[6 * D], u1.z, pdone); pdone = fmaf(mr[7 * D], u1.w, pdone);
   }
+  float pcur = 0.f;                                    // current group, frame gexpG
+  if (K > 0) {
+    const float4 u0 = *reinterpret_cast<const float4 *>(urow + 8 * G);
+    const float4 u1 = *reinterpret_cast<const float4 *>(urow + 8 * G + 4);
+    const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+    for (int k = 0; k < K; k++) pcur = fmaf(cur[k], uu[k], pcur);
+  }
+  const int df = max(st.CF, (K > 0) ? gexpG : kNegBig);
+  const float dm = fmaf(pdone, pow2i(st.CF - df), (K > 0) ? pcur * pow2i(gexpG - df) : 0.f);
   // (2) hand it to the next row; row 0 of the chunk takes the sum formed from the previous chunk's last row
   float rm = __shfl_up_sync(0xffffffffu, dm, 1);
   int rf = __shfl_up_sync(0xffffffffu, df, 1);
-  const float zm = __shfl_sync(0xffffffffu, d0m, CJ);
-  const int zf = __shfl_sync(0xffffffffu, d0f, CJ);
+  const float zm = __shfl_sync(0xffffffffu, d0m, cj);
+  const int zf = __shfl_sync(0xffffffffu, d0f, cj);
   if (lane == 0) { rm = zm; rf = zf; }
-  // (3) combine with the far sum (frame FI) -> total incoming mass of cell (row, CJ), frame Lm
-  const int jj = BETA ? (kBlk - 1 - CJ) : CJ;
-  const float X = xbw[jj];
+  // (3) combine with the far sum (frame FI) -> total incoming mass of the cell, frame Lm
+  const int jj = BETA ? (kBlk - 1 - cj) : cj;
+  const float X = mrow[jj];                            // far sum of this cell (its slot later takes the mantissa)
   const int Lm = max(FI, rf);
   const float tot = fmaf(X, pow2i(FI - Lm), rm * pow2i(rf - Lm));
   // (4) lattice value (off the dependency path)
@@ -165,65 +177,79 @@ __device__ __forceinline__ void chain_column(float (&mant)[kBlk], int (&gexp)[4]
   float out = neg_inf_f();
   if (valid && tot > 0.f) {
     const float fl = (float)Lm;
-    out = (mm[CJ & 7] + fmaf(__log2f(tot), 0.6931471805599453f, fl * kLn2Lo)) + fl * kLn2Hi;
+    out = (mm[K] + fmaf(__log2f(tot), 0.6931471805599453f, fl * kLn2Lo)) + fl * kLn2Hi;
     if (BETA) out += rmax_blk[jj];
   }
   iow[jj] = out;
-  // (5) outgoing mass of the cell = tot * emission * best transition, stored as mantissa in the group frame
-  const float v = tot * ew[CJ & 7];  // frame Lm + KE ; ew = 0 for invalid cells
+  // (5) outgoing mass = tot * emission * best transition, as a mantissa in the current group's frame
+  const float v = tot * ew[K];                         // frame Lm + KE ; ew = 0 for invalid cells
   float mnew = 0.f;
   if (v > 0.f) {
     const int fr = Lm + KE;
     const int e = fexp(v);
-    maxe = max(maxe, fr + e + 1);
-    const float vn = v * pow2i(-e);  // normalised to [1, 2)
-    if (gexp[G] == kNegBig) {
-      gexp[G] = fr + e;
+    const float vn = v * pow2i(-e);                    // normalised to [1, 2)
+    st.maxe = max(st.maxe, fr + e + 1);
+    if (gexpG == kNegBig) {
+      gexpG = fr + e;
       mnew = vn;
     } else {
-      const int shift = fr + e - gexp[G];
-      if (shift > 100) {  // the group frame is far too low for this value: re-frame the group (rare)
-        atomicAdd((unsigned long long *)&g_dp2_dbg[BETA ? 7 : 6], 1ull);
+      const int shift = fr + e - gexpG;
+      if (shift > 100) {                               // group frame far too low for this value: re-frame (rare)
 #pragma unroll
-        for (int c = G * 8; c < CJ; c++) mant[c] *= pow2i(-shift);
-        gexp[G] += shift;
+        for (int k = 0; k < K; k++) cur[k] *= pow2i(-shift);
+        gexpG += shift;
         mnew = vn;
       } else {
         mnew = vn * pow2i(shift);
       }
     }
   }
-  mant[CJ] = mnew;
+  cur[K] = mnew;
 }
 
-template <bool BETA, int CJ0>
-__device__ __forceinline__ void chain_group(float (&mant)[kBlk], int (&gexp)[4], int &maxe, const float *utw, float *iow,
-                                            const float *xbw, int lane, int FI, float d0m, int d0f, bool rowvalid,
-                                            int jbase, int t, int O, const float *rmax_blk) {
-  // emissions of this row for the 8 columns of the group: scaled exponentials and their integer frame
-  float mm[8], ew[8], w2[8];
-  float wmax = neg_inf_f();
+template <bool BETA>
+__device__ __forceinline__ void chain_sweep(ChainRow &st, const float *utw, float *mrow, float *iow, int lane, int FI,
+                                            float d0m, int d0f, bool rowvalid, int jbase, int t, int O,
+                                            const float *rmax_blk) {
+#pragma unroll 1
+  for (int G = 0; G < 4; G++) {
+    // emissions of this row for the 8 columns of the group: scaled exponentials and their integer frame
+    float mm[8], ew[8], w2[8];
+    float wmax = neg_inf_f();
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    const int cj = CJ0 + k;
-    const int jj = BETA ? (kBlk - 1 - cj) : cj;
-    const int j = jbase + jj;
-    const bool valid = rowvalid && j >= t && j < O;
-    mm[k] = iow[jj];
-    w2[k] = valid ? (mm[k] + rmax_blk[jj]) * kLog2e : neg_inf_f();
-    wmax = fmaxf(wmax, w2[k]);
+    for (int k = 0; k < 8; k++) {
+      const int cj = 8 * G + k;
+      const int jj = BETA ? (kBlk - 1 - cj) : cj;
+      const int j = jbase + jj;
+      const bool valid = rowvalid && j >= t && j < O;
+      mm[k] = iow[jj];
+      w2[k] = valid ? (mm[k] + rmax_blk[jj]) * kLog2e : neg_inf_f();
+      wmax = fmaxf(wmax, w2[k]);
+    }
+    const int KE = wmax > -1.0e30f ? (int)ceilf(wmax) : kNegBig;
+#pragma unroll
+    for (int k = 0; k < 8; k++) ew[k] = (KE > kNegBig) ? exp2f(w2[k] - (float)KE) : 0.f;
+    float cur[8];
+    int gexpG = kNegBig;
+    chain_column<BETA, 0>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 1>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 2>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 3>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 4>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 5>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 6>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    chain_column<BETA, 7>(cur, gexpG, st, G, utw, mrow, iow, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
+    // retire the group: bring everything completed so far to the common frame max(CF, gexpG)
+    const int nf = max(st.CF, gexpG);
+    if (nf > st.CF && st.CF > kNegBig) {
+      const float sc = pow2i(st.CF - nf);
+      for (int ci = 0; ci < 8 * G; ci++) mrow[BETA ? kBlk - 1 - ci : ci] *= sc;
+    }
+    const float sg = (gexpG > kNegBig) ? pow2i(gexpG - nf) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) mrow[BETA ? kBlk - 1 - (8 * G + k) : 8 * G + k] = cur[k] * sg;
+    st.CF = nf;
   }
-  const int KE = wmax > -1.0e30f ? (int)ceilf(wmax) : kNegBig;
-#pragma unroll
-  for (int k = 0; k < 8; k++) ew[k] = (KE > kNegBig) ? exp2f(w2[k] - (float)KE) : 0.f;
-  chain_column<BETA, CJ0 + 0>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 1>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 2>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 3>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 4>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 5>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 6>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
-  chain_column<BETA, CJ0 + 7>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, ew, mm, KE, rowvalid, jbase, t, O, rmax_blk);
 }
 
 // One direction of one utterance.
@@ -280,7 +306,7 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
       const int F = (int)ceilf(v2);
       const float mant0 = exp2f(v2 - (float)F);  // in (0.5, 1]
       sm.stm[q * kBlk + ci] = mant0;
-      sm.stf[q * 4 + (ci >> 3)] = F;
+      sm.stf[q] = F;
       sm.rmtab[seed_row * NB + q] = F + 1;
       // row 0 of the chunk-0 fragment tile of block q: value mant0/2 in frame F+1, at K index = vertex offset jj
       write_frag_elem(afrag + (size_t)q * 256, 0, jj, 0.5f * mant0);
@@ -459,60 +485,49 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
           const int t = BETA ? Tn - 2 - s : 1 + s;
           const float *utw = sm.ut + (size_t)ts * kBlk * kBlk;
           float *iow = sm.io + (size_t)ts * kRows * kPitch + lane * kPitch;
-          const float *xbw = sm.xbuf + (size_t)ts * kRows * kPitch + lane * kPitch;
           const int FI = sm.fbuf[ts * kRows + lane];
           const float *rmax_blk = sm.rmax + jbase;
 
-          // predecessor sums formed from the previous chunk's last row (the "row -1" of this tile): lane ci
-          // computes column ci, handed to lane 0 column by column inside chain_column
+          // predecessor sums formed from the previous chunk's last row (the "row -1" of this tile): lane cj
+          // computes column cj, handed to lane 0 column by column inside chain_column
           float d0m = 0.f;
           int d0f = kNegBig;
           {
             const float *pm = sm.stm + q * kBlk;
-            const int *pf = sm.stf + q * 4;
-            int f[4] = {pf[0], pf[1], pf[2], pf[3]};
-            float ps[4] = {0.f, 0.f, 0.f, 0.f};
+            d0f = sm.stf[q];
 #pragma unroll
             for (int c4 = 0; c4 < kBlk; c4 += 4) {  // U[ci][lane] (row `lane` of the staged weights), 0 for ci >= lane
               const float4 u4 = *reinterpret_cast<const float4 *>(utw + lane * kBlk + c4);
               const float4 m4 = *reinterpret_cast<const float4 *>(pm + c4);
-              float s_ = ps[c4 >> 3];
-              s_ = fmaf(m4.x, u4.x, s_); s_ = fmaf(m4.y, u4.y, s_); s_ = fmaf(m4.z, u4.z, s_); s_ = fmaf(m4.w, u4.w, s_);
-              ps[c4 >> 3] = s_;
+              d0m = fmaf(m4.x, u4.x, d0m); d0m = fmaf(m4.y, u4.y, d0m); d0m = fmaf(m4.z, u4.z, d0m); d0m = fmaf(m4.w, u4.w, d0m);
             }
-#pragma unroll
-            for (int g = 0; g < 4; g++) if (ps[g] > 0.f) d0f = max(d0f, f[g]);
-#pragma unroll
-            for (int g = 0; g < 4; g++) if (ps[g] > 0.f) d0m = fmaf(ps[g], pow2i(f[g] - d0f), d0m);
+            if (!(d0m > 0.f)) d0f = kNegBig;
           }
-          float mant[kBlk];
-          int gexp[4] = {kNegBig, kNegBig, kNegBig, kNegBig};
-          int maxe = kNegBig;
-          chain_group<BETA, 0>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
-          chain_group<BETA, 8>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
-          chain_group<BETA, 16>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
-          chain_group<BETA, 24>(mant, gexp, maxe, utw, iow, xbw, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
+          // my row of the far-sum tile doubles as the mantissa row (slot = vertex offset)
+          float *mrow = sm.xbuf + ((size_t)ts * kRows + lane) * kPitch;
+          ChainRow st;
+          st.CF = kNegBig;
+          st.maxe = kNegBig;
+          chain_sweep<BETA>(st, utw, mrow, iow, lane, FI, d0m, d0f, rowvalid, jbase, t, O, rmax_blk);
 
-          // frame table entry of my row, chain state of the chunk's last valid row
-          if (rowvalid) sm.rmtab[t * NB + q] = maxe;
+          // frame table entry of my row, chain state of the chunk's last valid row (one frame per block)
+          if (rowvalid) sm.rmtab[t * NB + q] = st.maxe;
           const int rl = min(kRows, nsteps - c * kRows) - 1;
           if (lane == rl) {
 #pragma unroll
-            for (int ci = 0; ci < kBlk; ci++) sm.stm[q * kBlk + ci] = mant[ci];
-#pragma unroll
-            for (int g = 0; g < 4; g++) sm.stf[q * 4 + g] = gexp[g];
+            for (int ci = 0; ci < kBlk; ci++) sm.stm[q * kBlk + ci] = mrow[BETA ? kBlk - 1 - ci : ci];
+            sm.stf[q] = st.CF;
           }
           // publish my row as A-operand for the tiles that will consume it as a previous row: normalised by the
           // row frame (value < 1), through shared memory into fragment order.  Producer step s feeds consumer row
           // (s + 1): rows 1..31 of this chunk's fragment tile, and row 0 of the next chunk's.
           {
-            float *vt = const_cast<float *>(sm.xbuf + (size_t)ts * kRows * kPitch);   // far sums are consumed: reuse
+            float *vt = sm.xbuf + (size_t)ts * kRows * kPitch;   // slots are already indexed by vertex offset = K index
+            const float nsc = (st.maxe > kNegBig && st.CF > kNegBig) ? pow2i(st.CF - st.maxe) : 0.f;
 #pragma unroll
-            for (int ci = 0; ci < kBlk; ci++) {
-              const int k = BETA ? (kBlk - 1 - ci) : ci;                               // K index = vertex offset
-              vt[lane * kPitch + k] = (maxe > kNegBig) ? mant[ci] * pow2i(gexp[ci >> 3] - maxe) : 0.f;
-            }
+            for (int k = 0; k < kBlk; k++) mrow[k] *= nsc;
             __syncwarp();
+            constexpr int VP = kPitch;
             uint4 *ft = afrag + ((size_t)c * NBv + q) * 256;
             const int fgid = lane >> 2, ftig = lane & 3;
 #pragma unroll
@@ -523,10 +538,10 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
                 const int rA = 16 * slice + fgid - 1, rB = rA + 8;
                 const int k0 = 16 * ks + 2 * ftig;
                 float e[8];
-                e[0] = rA >= 0 ? vt[rA * kPitch + k0] : 0.f;     e[1] = rA >= 0 ? vt[rA * kPitch + k0 + 1] : 0.f;
-                e[2] = vt[rB * kPitch + k0];                      e[3] = vt[rB * kPitch + k0 + 1];
-                e[4] = rA >= 0 ? vt[rA * kPitch + k0 + 8] : 0.f; e[5] = rA >= 0 ? vt[rA * kPitch + k0 + 9] : 0.f;
-                e[6] = vt[rB * kPitch + k0 + 8];                  e[7] = vt[rB * kPitch + k0 + 9];
+                e[0] = rA >= 0 ? vt[rA * VP + k0] : 0.f;     e[1] = rA >= 0 ? vt[rA * VP + k0 + 1] : 0.f;
+                e[2] = vt[rB * VP + k0];                      e[3] = vt[rB * VP + k0 + 1];
+                e[4] = rA >= 0 ? vt[rA * VP + k0 + 8] : 0.f; e[5] = rA >= 0 ? vt[rA * VP + k0 + 9] : 0.f;
+                e[6] = vt[rB * VP + k0 + 8];                  e[7] = vt[rB * VP + k0 + 9];
                 uint4 hi, lo;
                 split_bf16x2(e[0], e[1], hi.x, lo.x);
                 split_bf16x2(e[2], e[3], hi.y, lo.y);
@@ -549,8 +564,8 @@ __device__ void blocked_chain(const float *__restrict__ match, float *__restrict
               for (int ks = 0; ks < 2; ks++) {
                 const int k0 = 16 * ks + 2 * lane;   // lane = tig of (gid 0)
                 uint32_t h0, l0, h2, l2;
-                split_bf16x2(vt[31 * kPitch + k0], vt[31 * kPitch + k0 + 1], h0, l0);
-                split_bf16x2(vt[31 * kPitch + k0 + 8], vt[31 * kPitch + k0 + 9], h2, l2);
+                split_bf16x2(vt[31 * VP + k0], vt[31 * VP + k0 + 1], h0, l0);
+                split_bf16x2(vt[31 * VP + k0 + 8], vt[31 * VP + k0 + 9], h2, l2);
                 uint32_t *ph = reinterpret_cast<uint32_t *>(fn + (ks * 2 + 0) * 32 + lane);
                 uint32_t *pl = reinterpret_cast<uint32_t *>(fn + (ks * 2 + 1) * 32 + lane);
                 ph[0] = h0; ph[2] = h2; pl[0] = l0; pl[2] = l2;
