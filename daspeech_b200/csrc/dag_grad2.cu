@@ -39,6 +39,14 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void *
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
+__device__ __forceinline__ void split_bf16x2_g2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  float2 hf = __bfloat1622float2(h);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  lo = *reinterpret_cast<uint32_t *>(&l);
+}
+
 struct G2Planes {            // [level][hi/lo][kG2Kc][kG2Pitch]
   __nv_bfloat16 v[2][2][kG2Kc][kG2Pitch];
 };
@@ -78,6 +86,14 @@ grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ al
   // ---- tile maximum of the transitions (valid entries only) -------------------------------------------
   bool compute = !dead && i0 < O && n0 < O && (n0 + kG2Tile - 1 > i0);
   float emax = ninf;
+  if (compute) {  // pull the tile's transition rows towards L2: they are read now (maximum) and again in the epilogue
+    for (int x = tid; x < kG2Tile * 5; x += kG2Threads) {
+      const int ii = x / 5, seg = x % 5;
+      const int i = i0 + ii;
+      const int k = max(0, n0 - i - 1) + seg * 32;
+      if (i < O && k < Tl && k < n0 + kG2Tile - i - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(E + (int64_t)i * Tl + k));
+    }
+  }
   if (compute) {
     for (int ii = warp; ii < kG2Tile; ii += kG2Threads / 32) {
       const int i = i0 + ii;
@@ -179,28 +195,40 @@ grad_links_mma_kernel(const float *__restrict__ go, const float *__restrict__ al
       bool need1 = false;
 #pragma unroll
       for (int tr = 0; tr < kG2Kc; tr++) need1 = need1 || lev1_s[tr] != 0;
-      // operand planes: two exponent levels, bf16 hi/lo
-      for (int x = tid; x < kG2Kc * kG2Tile; x += kG2Threads) {
-        const int tr = x >> 7, c = x & 127;
+      // operand planes: two exponent levels, bf16 hi/lo; 4 consecutive vertices per thread-iteration
+      for (int x = tid; x < kG2Kc * kG2Tile / 4; x += kG2Threads) {
+        const int tr = x >> 5, c = (x & 31) * 4;
         const float u = u_s[tr];
-        float a0v = 0.f, a1v = 0.f, b0v = 0.f, b1v = 0.f;
-        if (u > ninf) {
-          const float xa = (i0 + c < O && stage_bi[x] > ninf) ? stage_a[x] - u : ninf;
-          if (xa >= -kG2Level) a0v = __expf(xa);
-          else if (xa > ninf) a1v = __expf(xa + kG2Level);
-          const float y = (n0 + c < O) ? stage_bn[x] + u + shift : ninf;
-          if (y > ninf) {
-            b0v = __expf(fminf(y, 80.f));
-            if (need1) b1v = __expf(fminf(y - kG2Level, 80.f));
-          }
+        const float4 av = *reinterpret_cast<const float4 *>(stage_a + tr * kG2Tile + c);
+        const float4 lv = *reinterpret_cast<const float4 *>(stage_bi + tr * kG2Tile + c);
+        const float4 bv = *reinterpret_cast<const float4 *>(stage_bn + tr * kG2Tile + c);
+        const float aa[4] = {av.x, av.y, av.z, av.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+        float a0[4], a1[4], b0[4], b1[4];
+        const bool rowlive = u > ninf;
+        const float ub = u + shift;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          // A: exp(alpha - u) for live vertices, split over the two levels
+          const float xa = (rowlive && i0 + c + e < O && ll[e] > ninf) ? aa[e] - u : ninf;
+          const bool hi_level = xa >= -kG2Level;
+          const float ea = __expf(hi_level ? xa : xa + kG2Level);        // exp(-inf) = 0
+          a0[e] = hi_level ? ea : 0.f;
+          a1[e] = hi_level ? 0.f : ea;
+          // B: exp(beta + u + Emax - Z), clamped
+          const float y = (rowlive && n0 + c + e < O) ? bb[e] + ub : ninf;
+          b0[e] = __expf(fminf(y, 80.f));
+          b1[e] = need1 ? __expf(fminf(y - kG2Level, 80.f)) : 0.f;
         }
-        const __nv_bfloat16 a0h = __float2bfloat16_rn(a0v), b0h = __float2bfloat16_rn(b0v);
-        pa->v[0][0][tr][c] = a0h; pa->v[0][1][tr][c] = __float2bfloat16_rn(a0v - __bfloat162float(a0h));
-        pb->v[0][0][tr][c] = b0h; pb->v[0][1][tr][c] = __float2bfloat16_rn(b0v - __bfloat162float(b0h));
+        uint2 h, l;
+        split_bf16x2_g2(a0[0], a0[1], h.x, l.x); split_bf16x2_g2(a0[2], a0[3], h.y, l.y);
+        *reinterpret_cast<uint2 *>(&pa->v[0][0][tr][c]) = h; *reinterpret_cast<uint2 *>(&pa->v[0][1][tr][c]) = l;
+        split_bf16x2_g2(b0[0], b0[1], h.x, l.x); split_bf16x2_g2(b0[2], b0[3], h.y, l.y);
+        *reinterpret_cast<uint2 *>(&pb->v[0][0][tr][c]) = h; *reinterpret_cast<uint2 *>(&pb->v[0][1][tr][c]) = l;
         if (need1) {
-          const __nv_bfloat16 a1h = __float2bfloat16_rn(a1v), b1h = __float2bfloat16_rn(b1v);
-          pa->v[1][0][tr][c] = a1h; pa->v[1][1][tr][c] = __float2bfloat16_rn(a1v - __bfloat162float(a1h));
-          pb->v[1][0][tr][c] = b1h; pb->v[1][1][tr][c] = __float2bfloat16_rn(b1v - __bfloat162float(b1h));
+          split_bf16x2_g2(a1[0], a1[1], h.x, l.x); split_bf16x2_g2(a1[2], a1[3], h.y, l.y);
+          *reinterpret_cast<uint2 *>(&pa->v[1][0][tr][c]) = h; *reinterpret_cast<uint2 *>(&pa->v[1][1][tr][c]) = l;
+          split_bf16x2_g2(b1[0], b1[1], h.x, l.x); split_bf16x2_g2(b1[2], b1[3], h.y, l.y);
+          *reinterpret_cast<uint2 *>(&pb->v[1][0][tr][c]) = h; *reinterpret_cast<uint2 *>(&pb->v[1][1][tr][c]) = l;
         }
       }
       __syncthreads();
