@@ -73,6 +73,13 @@ dag_prep_kernel(const float *__restrict__ links, const int64_t *__restrict__ ole
         dA[r * kBlk + lane] = tile[lane][r];                       // P'[ci][cj]
         dB[r * kBlk + lane] = tile[kBlk - 1 - r][kBlk - 1 - lane];  // P'[31-cj][31-ci]
       }
+      // fp64 push tables of the column-major kernel: [ci][cj] = weight of sweep column ci for the later column cj
+      double *pA = reinterpret_cast<double *>(base + lay.off_pushA) + (size_t)I * kBlk * kBlk;
+      double *pB = reinterpret_cast<double *>(base + lay.off_pushB) + (size_t)I * kBlk * kBlk;
+      for (int r = warp; r < kBlk; r += 8) {
+        pA[r * kBlk + lane] = (double)tile[r][lane];                          // P'[ci][cj]
+        pB[r * kBlk + lane] = (double)tile[kBlk - 1 - lane][kBlk - 1 - r];    // P'[31-cj][31-ci]
+      }
     } else {
       const int q = warp;  // 8 warps <-> 8 units
       const int qq = q & 3, ks = qq >> 1, nt0 = 2 * (qq & 1);

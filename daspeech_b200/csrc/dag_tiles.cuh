@@ -33,6 +33,10 @@ struct TileLayout {
   int NB;                // blocks per utterance
   int NC;                // 32-row chunks per utterance
   size_t off_rmax, off_diagA, off_diagB, off_tilesA, off_tilesB, off_afragA, off_afragB, sample_bytes;
+  // column-major kernel (dag_dp3.cu): fp64 in-block push tables [NB][ci][cj] (sweep order, weight of the already
+  // computed column ci for the later column cj) and the row handed from the last chunk of a pass to the first
+  // chunk of the next one: [2 (pass parity)][NB][32] fp64 predecessor sums + [2][NB] integer anchors
+  size_t off_pushA, off_pushB, off_passA, off_passB, off_passfA, off_passfB;
   __host__ __device__ static inline TileLayout make(int L, int M = 2) {
     TileLayout t;
     t.NB = (L + kBlk - 1) / kBlk;
@@ -48,6 +52,13 @@ struct TileLayout {
     // A-operand fragment cache of the recurrences: [chunk][block in sweep order] 4 KB each, per direction
     t.off_afragA = o; o += (size_t)t.NC * t.NB * kTileBytes;
     t.off_afragB = o; o += (size_t)t.NC * t.NB * kTileBytes;
+    o = (o + 255) & ~(size_t)255;
+    t.off_pushA = o;  o += (size_t)t.NB * kBlk * kBlk * sizeof(double);
+    t.off_pushB = o;  o += (size_t)t.NB * kBlk * kBlk * sizeof(double);
+    t.off_passA = o;  o += (size_t)2 * t.NB * kBlk * sizeof(double);
+    t.off_passB = o;  o += (size_t)2 * t.NB * kBlk * sizeof(double);
+    t.off_passfA = o; o += (((size_t)2 * t.NB * sizeof(int)) + 255) & ~(size_t)255;
+    t.off_passfB = o; o += (((size_t)2 * t.NB * sizeof(int)) + 255) & ~(size_t)255;
     t.sample_bytes = (o + 255) & ~(size_t)255;
     return t;
   }
