@@ -112,6 +112,13 @@ class ClockSampler:
         self._stop.set()
         if self._thr is not None:
             self._thr.join()
+        if self.nv is not None and not self.samples:   # the region was shorter than one NVML query
+            self._stop.clear()
+            self._stop.set()
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            except Exception:
+                pass
 
     def summary(self):
         s = sorted(self.samples)
@@ -268,12 +275,15 @@ def main():
     barrier()
     # ---- timed region: exactly K steps -------------------------------------------------------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for s in range(K):
+        alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
+        gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+    ev[1].record()
+    # The K steps are now queued on the stream (the host enqueues a step in < 0.1 ms, the GPU needs ~2 ms for it).
+    # Clocks / throttle reasons are sampled while the GPU works through them: NVML queries take the driver lock, so
+    # sampling WHILE launching would stall the launches and show up as idle gaps between kernels.
     with ClockSampler(local) as clk:
-        ev[0].record()
-        for s in range(K):
-            alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
-            gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
-        ev[1].record()
         barrier()
     elapsed_ms = ev[0].elapsed_time(ev[1])
     t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
@@ -299,14 +309,14 @@ def main():
         for i in range(5):
             prof[i] += max(buf[i], 0.0) / kp
     lib.dagb200_set_profile(0)
-    kern = {"dag_prep_kernel": prof[0], "dag_alpha_beta_blocked_kernel": prof[1],
-            "grad_match_kernel_v4": prof[2], "grad_links_mma_kernel": prof[3]}
+    kern = {"dag_prep_kernel": prof[0], "dag_alpha_beta_colmajor_kernel": prof[1],
+            "grad_planes_kernel": prof[2], "grad_links_planes_kernel": prof[3]}
     # algorithmic bytes of the launch each kernel belongs to: the forward pair
     # (precompute + recurrences) moves 4(3N+E), the backward pair 4(4N+2E)
     N_, E_ = B * M * L, B * L * T
-    kbytes = {"dag_alpha_beta_blocked_kernel": bytes_["fwd"], "grad_links_mma_kernel": 4 * (2 * N_ + 2 * E_),
-              "dag_prep_kernel": 4 * E_, "grad_match_kernel_v4": 4 * 4 * N_}
-    dom_name = max(("dag_alpha_beta_blocked_kernel", "grad_links_mma_kernel"), key=lambda n: kern[n])
+    kbytes = {"dag_alpha_beta_colmajor_kernel": bytes_["fwd"], "grad_links_planes_kernel": 4 * (2 * N_ + 2 * E_),
+              "dag_prep_kernel": 4 * E_, "grad_planes_kernel": 4 * 4 * N_}
+    dom_name = max(("dag_alpha_beta_colmajor_kernel", "grad_links_planes_kernel"), key=lambda n: kern[n])
     fwd_ms = prof[0] + prof[1]
     bwd_ms = prof[2] + prof[3]
     dom_ms = kern[dom_name]

@@ -147,13 +147,17 @@ class _DagKernel:
         links = links.contiguous()
         grad_match_all = torch.empty_like(alpha)
         grad_links = torch.empty((bsz, prelen, translen), dtype=match_all.dtype, device=match_all.device)
+        nbytes = 0
+        if EXACT_LOG_DOMAIN is False and match_all.dtype == torch.float32:
+            nbytes = int(self.lib.dagb200_dag_loss_backward_workspace_bytes(bsz, tarlen, prelen, translen))
+        workspace = self._workspace(nbytes, match_all.device)
         self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(match_all.device):
-            rc = self.lib.dagb200_dag_loss_backward(_ptr(grad_output), _ptr(alpha), _ptr(beta), _ptr(match_all),
-                                                    _ptr(links), _ptr(output_length), _ptr(target_length),
-                                                    _ptr(grad_match_all), _ptr(grad_links),
-                                                    _DTYPE_CODE[match_all.dtype], bsz, tarlen, prelen, translen,
-                                                    int(config1), int(config2), _stream())
+            rc = self.lib.dagb200_dag_loss_backward_ws(_ptr(grad_output), _ptr(alpha), _ptr(beta), _ptr(match_all),
+                                                       _ptr(links), _ptr(output_length), _ptr(target_length),
+                                                       _ptr(grad_match_all), _ptr(grad_links),
+                                                       _DTYPE_CODE[match_all.dtype], bsz, tarlen, prelen, translen,
+                                                       int(config1), int(config2), _ptr(workspace), nbytes, _stream())
         _lib.check(rc, "dag_loss_backward")
         return grad_match_all, grad_links
 

@@ -114,6 +114,19 @@ int dagb200_dag_loss_backward(const void *grad_output, const void *alpha, const 
                               void *grad_match, void *grad_links, int dtype,
                               int B, int M, int L, int T, int config1, int config2, void *stream);
 
+/* Same contract as dagb200_dag_loss_backward, plus a device scratch of
+ * dagb200_dag_loss_backward_workspace_bytes(B,M,L,T) bytes.  With it (fp32, not in exact mode) the backward runs as
+ * two passes (dag_grad3.cu): one streaming pass that writes grad_match and bf16 hi/lo operand planes of exp(alpha),
+ * exp(beta) with one integer frame per (row, 32-vertex block), and a tensor-core contraction over the target index
+ * for grad_links.  With workspace == NULL it is exactly dagb200_dag_loss_backward.                        */
+size_t dagb200_dag_loss_backward_workspace_bytes(int B, int M, int L, int T);
+int dagb200_dag_loss_backward_ws(const void *grad_output, const void *alpha, const void *beta,
+                                 const void *match, const void *links,
+                                 const int64_t *output_length, const int64_t *target_length,
+                                 void *grad_match, void *grad_links, int dtype,
+                                 int B, int M, int L, int T, int config1, int config2,
+                                 void *workspace, size_t workspace_bytes, void *stream);
+
 /* Replaces `dag_best_alignment` (dag_loss.cpp:21, dag_best_alignment.cu:209-253).
  *   alpha [B][M][L] (max-plus scores) may be NULL when the caller discards it (the reference's
  *   Python wrapper does, dag_loss.py:227-230); path int32 [B][L], -1 = vertex not on the path.
