@@ -194,7 +194,8 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
 
   // shared memory: operand stages | per-warp scale tables [8][Mp] bf16 | per-pair epilogue exponents
   Stage *stg = reinterpret_cast<Stage *>(g3_smem);
-  __nv_bfloat16 *stab = reinterpret_cast<__nv_bfloat16 *>(g3_smem + kStages * sizeof(Stage));   // [8][Mp]
+  int *fsum = reinterpret_cast<int *>(g3_smem + kStages * sizeof(Stage));                       // [8][Mp]
+  __nv_bfloat16 *stab = reinterpret_cast<__nv_bfloat16 *>(fsum + 8 * Mp);                       // [8][Mp]
   float *dpair = reinterpret_cast<float *>(stab + 8 * Mp);                         // [8]
   float *cs = reinterpret_cast<float *>(g3_smem);                                  // [128][kCP] after the K loop
 
@@ -216,6 +217,13 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
     const int *FA = reinterpret_cast<const int *>(ws + pl.off_fa) + (size_t)b * M * pl.NBp;
     const int *FB = reinterpret_cast<const int *>(ws + pl.off_fb) + (size_t)b * M * pl.NBp;
     const int nchunks = (nsteps + kKc - 1) / kKc;
+    // pull my links tile (read by the epilogue) towards L2: 128 rows x 256 bytes, 3 lines per row cover the segment
+    for (int x = tid; x < kBI * 3; x += kThreads) {
+      const int ii = x / 3, seg = x % 3;
+      const int i = i0 + ii;
+      const int k = max(0, n0 - i - 1) + seg * 32;
+      if (i < O && k < Tl && k < n0 + kBN - i - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(E + (int64_t)i * Tl + k));
+    }
 
     // one chunk of 16 target rows: A rows t, B rows t + 1, 768 16-byte cp.async granules = 3 per thread with fixed
     // (row, plane, column) roles, so the addressing is done once
@@ -258,15 +266,20 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
       else asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    // per-pair scale table: 2^(FA[t] + FB[t+1] - Fmax) as bf16 (exact), and the epilogue exponent Fmax - Z log2e;
-    // the frames of my pair go straight from global memory into registers (8 rows per lane at a time)
+    // per-pair scale table: 2^(FA[t] + FB[t+1] - Fmax) as bf16 (exact), and the epilogue exponent Fmax - Z log2e.
+    // One batched pass over the frames of my pair (global -> per-warp shared table), then the conversion in place.
     {
       const int blkI = i0 / 32 + wi, blkN = n0 / 32 + wn;
+      int *sums = fsum + warp * Mp;
       __nv_bfloat16 *st = stab + warp * Mp;
       int fmx = kNegBig;
-      for (int t = lane; t < nsteps; t += 32) {
-        const int x = __ldg(FA + (size_t)t * pl.NBp + blkI), y = __ldg(FB + (size_t)(t + 1) * pl.NBp + blkN);
+      const int *pa = FA + blkI + (size_t)lane * pl.NBp, *pb = FB + blkN + (size_t)(lane + 1) * pl.NBp;
+      const size_t step = (size_t)32 * pl.NBp;
+#pragma unroll 4
+      for (int t = lane; t < nsteps; t += 32, pa += step, pb += step) {
+        const int x = __ldg(pa), y = __ldg(pb);
         const int sum = (x > kNegBig && y > kNegBig) ? x + y : kNegBig;
+        sums[t] = sum;
         fmx = max(fmx, sum);
       }
       fmx = __reduce_max_sync(0xffffffffu, fmx);
@@ -274,11 +287,8 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
       for (int t = lane; t < mpad; t += 32) {
         unsigned short bits = 0;
         if (t < nsteps) {
-          const int x = __ldg(FA + (size_t)t * pl.NBp + blkI), y = __ldg(FB + (size_t)(t + 1) * pl.NBp + blkN);
-          if (x > kNegBig && y > kNegBig) {
-            const int d = x + y - fmx;                       // <= 0
-            if (d >= -126) bits = (unsigned short)((d + 127) << 7);
-          }
+          const int d = sums[t] - fmx;                         // <= 0 (or hugely negative: no mass)
+          if (d >= -126) bits = (unsigned short)((d + 127) << 7);
         }
         st[t] = __ushort_as_bfloat16(bits);
       }
@@ -346,12 +356,23 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
     __syncthreads();
   }
 
-  // ---- epilogue: gl = go * exp2(links * log2e + Fmax - Z log2e) * G, one coalesced write per row, zeros elsewhere
+  // ---- epilogue: gl = go * exp2(links * log2e + Fmax - Z log2e) * G, one coalesced write per row, zeros elsewhere.
+  // A warp owns 16 rows; their 32 transition values are fetched first (independent loads), then combined.
   const bool last_col = (n0 + kBN >= L);
-  for (int ii = warp; ii < kBI; ii += kThreads / 32) {
-    const int i = i0 + ii;
+  float lk[16][2];
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    const int ii = warp + 8 * r, i = i0 + ii;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int n = n0 + lane + 32 * h, k = n - i - 1;
+      lk[r][h] = (compute && i < O && n < O && k >= 0 && k < Tl) ? __ldg(E + (int64_t)i * Tl + k) : neg_inf_f();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    const int ii = warp + 8 * r, i = i0 + ii;
     if (i >= L) break;
-    const float *erow = E + (int64_t)i * Tl;
     float *grow = g + (int64_t)i * Tl;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -359,10 +380,7 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
       const int n = n0 + nn, k = n - i - 1;
       if (k < 0 || k >= Tl) continue;
       float v = 0.f;
-      if (compute && i < O && n < O) {
-        const float x = fmaf(__ldg(erow + k), kL2E, dpair[(ii >> 5) * 2 + h]);
-        v = gout * exp2f(x) * cs[ii * kCP + nn];
-      }
+      if (compute && i < O && n < O) v = gout * exp2f(fmaf(lk[r][h], kL2E, dpair[(ii >> 5) * 2 + h])) * cs[ii * kCP + nn];
       grow[k] = v;
     }
     if (last_col) {  // transitions that point beyond the padded graph: k >= L-1-i
@@ -374,7 +392,7 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
 int padded_rows(int M) { return (M + 15) / 16 * 16; }
 size_t mma_smem_bytes(int M) {
   const int Mp = padded_rows(M);
-  const size_t a = kStages * sizeof(Stage) + (size_t)8 * Mp * 2 + 8 * sizeof(float) + 64;
+  const size_t a = kStages * sizeof(Stage) + (size_t)8 * Mp * 6 + 8 * sizeof(float) + 64;
   const size_t c = sizeof(float) * kBI * kCP;
   return a > c ? a : c;
 }
