@@ -270,8 +270,11 @@ def main():
         gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
         return alpha, beta, gm, gl
 
+    # warm-up with exactly the allocation pattern of the timed loop (same names kept alive), so that the caching
+    # allocator is in steady state and no cudaMalloc (a device-wide sync) lands inside the timed region
     for _ in range(W):
-        out = step()
+        alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
+        gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
     barrier()
     # ---- timed region: exactly K steps -------------------------------------------------------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -293,7 +296,7 @@ def main():
     ms_per_step = elapsed_ms / K
     cells = B * M * L * world
     value = cells / (ms_per_step * 1e-3)
-    loss_check = float(out[1][:, 0, 0].float().mean().item())
+    loss_check = float(beta[:, 0, 0].float().mean().item())
 
     # ---- per-kernel durations: CUDA events recorded by the library on the launch stream around each of its
     # kernels (dagb200_set_profile), averaged over a few extra steps right after the timed region -----------
@@ -309,13 +312,13 @@ def main():
         for i in range(5):
             prof[i] += max(buf[i], 0.0) / kp
     lib.dagb200_set_profile(0)
-    kern = {"dag_prep_kernel": prof[0], "dag_alpha_beta_colmajor_kernel": prof[1],
+    kern = {"dag_rowmax_kernel+dag_tiles_kernel": prof[0], "dag_alpha_beta_colmajor_kernel": prof[1],
             "grad_planes_kernel": prof[2], "grad_links_planes_kernel": prof[3]}
     # algorithmic bytes of the launch each kernel belongs to: the forward pair
     # (precompute + recurrences) moves 4(3N+E), the backward pair 4(4N+2E)
     N_, E_ = B * M * L, B * L * T
     kbytes = {"dag_alpha_beta_colmajor_kernel": bytes_["fwd"], "grad_links_planes_kernel": 4 * (2 * N_ + 2 * E_),
-              "dag_prep_kernel": 4 * E_, "grad_planes_kernel": 4 * 4 * N_}
+              "dag_rowmax_kernel+dag_tiles_kernel": 4 * E_, "grad_planes_kernel": 4 * 4 * N_}
     dom_name = max(("dag_alpha_beta_colmajor_kernel", "grad_links_planes_kernel"), key=lambda n: kern[n])
     fwd_ms = prof[0] + prof[1]
     bwd_ms = prof[2] + prof[3]
@@ -356,7 +359,7 @@ def main():
         h_loss.copy_(loss.detach(), non_blocking=True)
         return m.grad, lk.grad
 
-    del out, alpha, beta, gm, gl
+    del alpha, beta, gm, gl
     e2e_k = max(3, min(K, 10))
     for _ in range(3):
         e2e_step()
@@ -415,7 +418,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, T),
                 "utt_per_sec": B * world / (ms_per_step * 1e-3), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": 4 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
+                "gpu_launches": 5 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, T)
         print(json.dumps(line), flush=True)

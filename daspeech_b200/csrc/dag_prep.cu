@@ -22,71 +22,86 @@ __device__ __forceinline__ uint32_t frag_reg(F bop, int ks, int nt, int r, int g
   return pack_bf16_pair(x0, x1);
 }
 
+// pass 1: per-source-vertex maximum over the valid successors (one warp per vertex, coalesced along k)
 __global__ void __launch_bounds__(256)
-dag_prep_kernel(const float *__restrict__ links, const int64_t *__restrict__ olen, unsigned char *__restrict__ ws,
-                int L, int Tl, TileLayout lay) {
-  __shared__ float tile[kBlk][kBlk + 1];
-  __shared__ float s_rmax[kBlk];
-  const int I = blockIdx.x, b = blockIdx.y;
+dag_rowmax_kernel(const float *__restrict__ links, const int64_t *__restrict__ olen, unsigned char *__restrict__ ws,
+                  int L, int Tl, TileLayout lay) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= lay.NB * kBlk) return;
   const int O = min((int)olen[b], L);
-  if (32 * I >= O) return;  // block beyond the graph: never read by the recurrences
+  float mx = neg_inf_f();
+  if (i < O) {
+    const int kmax = min(Tl, O - 1 - i);
+    const float *row = links + ((int64_t)b * L + i) * Tl;
+    float m0 = mx, m1 = mx, m2 = mx, m3 = mx;
+    int k = lane;
+    for (; k + 96 < kmax; k += 128) {
+      m0 = fmaxf(m0, __ldg(row + k)); m1 = fmaxf(m1, __ldg(row + k + 32));
+      m2 = fmaxf(m2, __ldg(row + k + 64)); m3 = fmaxf(m3, __ldg(row + k + 96));
+    }
+    for (; k < kmax; k += 32) m0 = fmaxf(m0, __ldg(row + k));
+    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) reinterpret_cast<float *>(ws + (size_t)b * lay.sample_bytes + lay.off_rmax)[i] = mx;
+}
+
+// pass 2: one CTA (4 warps) per 32x32 tile (I <= J): P' = exp(links - rmax) into the operand layouts
+__global__ void __launch_bounds__(128)
+dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ olen, unsigned char *__restrict__ ws,
+                 int L, int Tl, TileLayout lay) {
+  __shared__ float tile[kBlk][kBlk + 1];
+  const int I = blockIdx.y, b = blockIdx.z;
+  const int J = I + blockIdx.x;                    // blockIdx.x = block distance, 0 .. band
+  const int O = min((int)olen[b], L);
+  if (32 * I >= O) return;                         // block beyond the graph: never read by the recurrences
+  const int NBv = (O + kBlk - 1) / kBlk;
+  if (J > min(NBv - 1, I + band_blocks(Tl))) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float *E = links + (int64_t)b * L * Tl;
   unsigned char *base = ws + (size_t)b * lay.sample_bytes;
-  float *g_rmax = reinterpret_cast<float *>(base + lay.off_rmax);
-
-  // phase 1: row maxima over the valid successors of each source vertex of this block
-  for (int ii = warp; ii < kBlk; ii += 8) {
+  const float *g_rmax = reinterpret_cast<const float *>(base + lay.off_rmax);
+  // the 32x32 tile of P' in shared memory (row = source ii, column = destination jj); 8 rows per warp, all loads first
+  float v[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int ii = warp * 8 + r;
+    const int i = 32 * I + ii, j = 32 * J + lane, k = j - i - 1;
+    v[r] = (i < O && j < O && k >= 0 && k < Tl) ? __ldg(E + (int64_t)i * Tl + k) : neg_inf_f();
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int ii = warp * 8 + r;
     const int i = 32 * I + ii;
-    float mx = neg_inf_f();
-    if (i < O) {
-      const int kmax = min(Tl, O - 1 - i);
-      const float *row = E + (int64_t)i * Tl;
-      for (int k = lane; k < kmax; k += 32) mx = fmaxf(mx, __ldg(row + k));
-    }
-    mx = warp_max(mx);
-    if (lane == 0) { s_rmax[ii] = mx; g_rmax[i < lay.NB * kBlk ? i : 0] = mx; }
+    const float rm = i < O ? g_rmax[i] : neg_inf_f();
+    tile[ii][lane] = __expf(v[r] - (rm == neg_inf_f() ? 0.f : rm));   // exp(-inf) = 0
   }
   __syncthreads();
-
-  const int NBv = (O + kBlk - 1) / kBlk;
-  const int Jend = min(NBv - 1, I + band_blocks(Tl));
   const int gid = lane >> 2, tig = lane & 3;
-  for (int J = I; J <= Jend; J++) {
-    // phase 2a: the 32x32 tile of P' in shared memory (row = source ii, column = destination jj)
-    for (int ii = warp; ii < kBlk; ii += 8) {
-      const int i = 32 * I + ii, j = 32 * J + lane, k = j - i - 1;
-      float p = 0.f;
-      if (i < O && j < O && k >= 0 && k < Tl) {
-        const float rm = s_rmax[ii];
-        p = __expf(__ldg(E + (int64_t)i * Tl + k) - (rm == neg_inf_f() ? 0.f : rm));
-      }
-      tile[ii][lane] = p;
+  if (J == I) {
+    float *dA = reinterpret_cast<float *>(base + lay.off_diagA) + (size_t)I * kBlk * kBlk;
+    float *dB = reinterpret_cast<float *>(base + lay.off_diagB) + (size_t)I * kBlk * kBlk;
+    double *pA = reinterpret_cast<double *>(base + lay.off_pushA) + (size_t)I * kBlk * kBlk;
+    double *pB = reinterpret_cast<double *>(base + lay.off_pushB) + (size_t)I * kBlk * kBlk;
+    for (int r = warp; r < kBlk; r += 4) {
+      // fp32 [cj][ci] = weight of in-block predecessor ci for cell cj (sweep order; zero for ci >= cj)
+      dA[r * kBlk + lane] = tile[lane][r];                                   // P'[ci][cj]
+      dB[r * kBlk + lane] = tile[kBlk - 1 - r][kBlk - 1 - lane];              // P'[31-cj][31-ci]
+      // fp64 push tables [ci][cj] = weight of sweep column ci for the later column cj
+      pA[r * kBlk + lane] = (double)tile[r][lane];                            // P'[ci][cj]
+      pB[r * kBlk + lane] = (double)tile[kBlk - 1 - lane][kBlk - 1 - r];      // P'[31-cj][31-ci]
     }
-    __syncthreads();
-    if (J == I) {
-      float *dA = reinterpret_cast<float *>(base + lay.off_diagA) + (size_t)I * kBlk * kBlk;
-      float *dB = reinterpret_cast<float *>(base + lay.off_diagB) + (size_t)I * kBlk * kBlk;
-      // [cj][ci] = weight of in-block predecessor ci for cell cj, both in sweep order (alpha: ascending vertex,
-      // beta: descending vertex), zero for ci >= cj
-      for (int r = warp; r < kBlk; r += 8) {
-        dA[r * kBlk + lane] = tile[lane][r];                       // P'[ci][cj]
-        dB[r * kBlk + lane] = tile[kBlk - 1 - r][kBlk - 1 - lane];  // P'[31-cj][31-ci]
-      }
-      // fp64 push tables of the column-major kernel: [ci][cj] = weight of sweep column ci for the later column cj
-      double *pA = reinterpret_cast<double *>(base + lay.off_pushA) + (size_t)I * kBlk * kBlk;
-      double *pB = reinterpret_cast<double *>(base + lay.off_pushB) + (size_t)I * kBlk * kBlk;
-      for (int r = warp; r < kBlk; r += 8) {
-        pA[r * kBlk + lane] = (double)tile[r][lane];                          // P'[ci][cj]
-        pB[r * kBlk + lane] = (double)tile[kBlk - 1 - lane][kBlk - 1 - r];    // P'[31-cj][31-ci]
-      }
-    } else {
-      const int q = warp;  // 8 warps <-> 8 units
+  } else {
+    uint4 *tA = reinterpret_cast<uint4 *>(base + lay.off_tilesA + lay.idxA(I, J) * kTileBytes);
+    uint4 *tB = reinterpret_cast<uint4 *>(base + lay.off_tilesB + lay.idxB(I, J) * kTileBytes);
+    auto bopA = [&](int k, int n) { return tile[k][n]; };  // K = source, N = destination
+    auto bopB = [&](int k, int n) { return tile[n][k]; };  // K = destination, N = source
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int q = warp * 2 + u;  // 4 warps x 2 <-> 8 units
       const int qq = q & 3, ks = qq >> 1, nt0 = 2 * (qq & 1);
-      uint4 *tA = reinterpret_cast<uint4 *>(base + lay.off_tilesA + lay.idxA(I, J) * kTileBytes);
-      uint4 *tB = reinterpret_cast<uint4 *>(base + lay.off_tilesB + lay.idxB(I, J) * kTileBytes);
-      auto bopA = [&](int k, int n) { return tile[k][n]; };  // K = source, N = destination
-      auto bopB = [&](int k, int n) { return tile[n][k]; };  // K = destination, N = source
       uint4 ua, ub;
       if (q < 4) {
         ua.x = frag_reg<false>(bopA, ks, nt0, 0, gid, tig); ua.y = frag_reg<false>(bopA, ks, nt0, 1, gid, tig);
@@ -102,15 +117,22 @@ dag_prep_kernel(const float *__restrict__ links, const int64_t *__restrict__ ole
       tA[q * 32 + lane] = ua;
       tB[q * 32 + lane] = ub;
     }
-    __syncthreads();
   }
 }
 
 int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, cudaStream_t st) {
   TileLayout lay = TileLayout::make(L, M);
-  dim3 grid(lay.NB, B);
-  dag_prep_kernel<<<grid, 256, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay);
-  DAGB200_CHECK_LAUNCH("dag_prep_kernel");
+  {
+    dim3 grid((lay.NB * kBlk + 7) / 8, B);
+    dag_rowmax_kernel<<<grid, 256, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay);
+    DAGB200_CHECK_LAUNCH("dag_rowmax_kernel");
+  }
+  {
+    const int nd = min(lay.NB, band_blocks(Tl) + 1);
+    dim3 grid(nd, lay.NB, B);
+    dag_tiles_kernel<<<grid, 128, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay);
+    DAGB200_CHECK_LAUNCH("dag_tiles_kernel");
+  }
   return 0;
 }
 
