@@ -423,15 +423,16 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
 namespace dagb200 {
 bool vit2_supported(int M, int L);
 int launch_viterbi_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
-                           float *lattice, uint16_t *trace, int32_t *path, int B, int M, int L, int Tl,
-                           int32_t *status, cudaStream_t st);
+                           float *lattice, uint16_t *trace, int32_t *path, unsigned char *flags, int B, int M, int L,
+                           int Tl, int32_t *status, cudaStream_t st);
 }  // namespace dagb200
 
 // trace (uint16 per cell) + a lattice plane for the case the caller does not want alpha back
 extern "C" size_t dagb200_best_alignment_workspace_bytes(int B, int M, int L, int T) {
   (void)T;
   const size_t cells = (size_t)B * M * L;
-  return ((cells * sizeof(uint16_t) + 255) & ~(size_t)255) + cells * sizeof(float);
+  const size_t flags = ((size_t)B * M * ((L + 31) / 32) + 255) & ~(size_t)255;   // per (row, 32-vertex block) flags
+  return ((cells * sizeof(uint16_t) + 255) & ~(size_t)255) + ((cells * sizeof(float) + 255) & ~(size_t)255) + flags;
 }
 
 extern "C" int dagb200_dag_best_alignment(const void *match, const void *links, const int64_t *output_length,
@@ -451,8 +452,10 @@ extern "C" int dagb200_dag_best_alignment(const void *match, const void *links, 
     const size_t cells = (size_t)B * M * L;
     float *lattice = alpha ? (float *)alpha
                            : reinterpret_cast<float *>((unsigned char *)workspace + ((cells * sizeof(uint16_t) + 255) & ~(size_t)255));
+    unsigned char *flags = (unsigned char *)workspace + ((cells * sizeof(uint16_t) + 255) & ~(size_t)255) +
+                           ((cells * sizeof(float) + 255) & ~(size_t)255);
     return launch_viterbi_blocked((const float *)match, (const float *)links, output_length, target_length, lattice,
-                                  (uint16_t *)workspace, path, B, M, L, T, status, st);
+                                  (uint16_t *)workspace, path, flags, B, M, L, T, status, st);
   }
   if (dtype == DAGB200_F32)
     return launch_viterbi<float>((const float *)match, (const float *)links, output_length, target_length,

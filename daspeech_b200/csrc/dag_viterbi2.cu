@@ -12,6 +12,8 @@
 // per utterance.  Far predecessors: lanes = destination columns, the 32x32 transition tile column lives in
 // registers and is reused for 16 rows (the reference re-reads every transition for every row); near
 // predecessors: lanes = rows, serial sweep over the 32 columns, one shuffle per column.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dagb200 {
@@ -343,6 +345,248 @@ dag_viterbi_blocked_kernel(const float *__restrict__ match, const float *__restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Two CTAs per utterance (one thread-block cluster): the tiles of an anti-diagonal wave are independent, so the
+// chunks of a wave are split by parity between the two CTAs of the cluster -- 128 CTAs instead of 64 at B = 64.
+// Everything a tile needs from another tile already travels through global memory (lattice rows, back-pointers);
+// the per-(row, block) "has a finite value" flags move to global memory as well, and one cluster barrier
+// (release / acquire) per wave publishes a wave's results to both CTAs.  Far phase: 4 warps x 8 rows per tile.
+constexpr int kVcTpw = kV2Warps / 4;     // tiles per batch per CTA
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1)
+dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restrict__ links,
+                           const int64_t *__restrict__ olen, const int64_t *__restrict__ tlen,
+                           float *lattice, uint16_t *trace, int32_t *__restrict__ path,
+                           unsigned char *gflags, int M, int L, int Tl, int NB, int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char v2_smem[];
+  const int b = blockIdx.x >> 1, rank = blockIdx.x & 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int O = (int)olen[b], Tn = (int)tlen[b];
+  const int64_t latsz = (int64_t)M * L;
+  const float ninf = neg_inf_f();
+  float *lat = lattice + b * latsz;
+  uint16_t *trg = trace + b * latsz;
+  int32_t *prow = path + (int64_t)b * L;
+  const float *m = match + b * latsz;
+  const float *E = links + (int64_t)b * L * Tl;
+  unsigned char *flag = gflags + (size_t)b * M * NB;
+  if (rank == 0)
+    for (int j = threadIdx.x; j < L; j += kV2Threads) prow[j] = -1;
+
+  int st = DAGB200_ST_OK;
+  if (Tn < 2 || O < 2) st = DAGB200_ST_LEN_LT2;
+  else if (O < Tn || O > L || Tn > M) st = DAGB200_ST_GRAPH_SMALL;
+  else if ((int64_t)(Tn - 1) * Tl + 1 < O) st = DAGB200_ST_TOO_SHORT;
+  if (st != DAGB200_ST_OK) {   // both CTAs of the cluster leave together: no barrier is pending
+    if (rank == 0) {
+      for (int64_t x = threadIdx.x; x < latsz; x += kV2Threads) lat[x] = ninf;
+      if (status && threadIdx.x == 0) status[b] = st;
+    }
+    return;
+  }
+
+  float *s_ed, *s_xv, *s_io, *s_vs;
+  int *s_xd;
+  {
+    float *p = reinterpret_cast<float *>(v2_smem);
+    s_ed = p;  p += kVcTpw * kVB * kVB;
+    s_xv = p;  p += kVcTpw * kVB * kV2Pitch;
+    s_xd = reinterpret_cast<int *>(p);  p += kVcTpw * kVB * kV2Pitch;
+    s_io = p;  p += kVcTpw * kVB * kV2Pitch;
+    s_vs = p;
+  }
+  const int NBv = (O + kVB - 1) / kVB;
+  const int nsteps = Tn - 1;
+  const int NCv = (nsteps + kVB - 1) / kVB;
+  const int band = 1 + (Tl - 1) / kVB;
+
+  // prologue (split between the two CTAs): flags, padding, seed row
+  if (rank == 1) {
+    for (int x = threadIdx.x; x < M * NB; x += kV2Threads) flag[x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0 && m[0] > ninf) flag[0] = 1;
+  } else {
+    const int64_t tail0 = (int64_t)Tn * L;
+    for (int64_t x = tail0 + threadIdx.x; x < latsz; x += kV2Threads) lat[x] = ninf;
+    const int c0 = NBv * kVB;
+    if (c0 < L) {
+      const int wcols = L - c0;
+      for (int x = threadIdx.x; x < Tn * wcols; x += kV2Threads) lat[(int64_t)(x / wcols) * L + c0 + x % wcols] = ninf;
+    }
+    for (int j = threadIdx.x; j < min(L, c0); j += kV2Threads) lat[j] = (j == 0) ? m[0] : ninf;
+  }
+  cluster_sync_all();
+
+  const int nwaves = NBv + NCv - 1;
+  for (int w = 0; w < nwaves; w++) {
+    const int c_lo = max(0, w - NBv + 1), c_hi = min(NCv - 1, w);
+    const int c_first = c_lo + ((c_lo ^ rank) & 1);          // my chunks: parity = rank
+    for (int cb = c_first; cb <= c_hi; cb += 2 * kVcTpw) {
+      // ======================= far phase: lanes = destination columns, 8 rows per warp =======================
+      {
+        const int ts = warp >> 2, sl = warp & 3;
+        const int c = cb + 2 * ts;
+        if (c <= c_hi) {
+          const int J = w - c;
+          const int j = kVB * J + lane;
+          {
+            float *edw = s_ed + (size_t)ts * kVB * kVB;
+            float *iow = s_io + (size_t)ts * kVB * kV2Pitch;
+            for (int rr = sl; rr < kVB; rr += 4) {
+              const int i = kVB * J + rr, k = lane - rr - 1;
+              if (k >= 0 && k < Tl && i < O && j < O) cp_async_f32_v(edw + lane * kVB + rr, E + (int64_t)i * Tl + k);
+              else edw[lane * kVB + rr] = ninf;
+              const int s = c * kVB + rr;
+              if (s < nsteps && j < L) cp_async_f32_v(iow + rr * kV2Pitch + lane, m + (int64_t)(1 + s) * L + j);
+              else iow[rr * kV2Pitch + lane] = ninf;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
+          float *xvw = s_xv + (size_t)ts * kVB * kV2Pitch + (8 * sl) * kV2Pitch + lane;
+          int *xdw = s_xd + (size_t)ts * kVB * kV2Pitch + (8 * sl) * kV2Pitch + lane;
+#pragma unroll
+          for (int rr = 0; rr < 8; rr++) { xvw[rr * kV2Pitch] = ninf; xdw[rr * kV2Pitch] = 0; }
+          float *vsw = s_vs + (size_t)warp * 8 * kVB;
+          const int s_first = c * kVB + 8 * sl;            // previous-row index of my first row
+          const int qlo = max(0, J - band);
+          for (int I = qlo; I < J; I++) {
+            bool any = false;
+            if (lane < 8 && s_first + lane < nsteps) any = __ldcg(flag + (s_first + lane) * NB + I) != 0;
+            if (!__any_sync(0xffffffffu, any)) continue;
+            float ecol[kVB];
+#pragma unroll
+            for (int ii = 0; ii < kVB; ii++) {
+              const int i = kVB * I + ii, k = j - i - 1;
+              ecol[ii] = (k < Tl && j < O) ? __ldg(E + (int64_t)i * Tl + k) : ninf;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+              const int tp = s_first + rr;
+              vsw[rr * kVB + lane] = (tp < nsteps) ? __ldcg(lat + (int64_t)tp * L + kVB * I + lane) : ninf;
+            }
+            __syncwarp();
+            const int dbase = kVB * (J - I) + lane;
+            int ord[4];
+#pragma unroll
+            for (int r4 = 0; r4 < 4; r4++) ord[r4] = (dbase - 1 - (((r4 & 1) << 1) | (r4 >> 1))) & 3;
+            for (int rr = 0; rr < 8; rr++) {
+              float bv0 = ninf, bv1 = ninf, bv2 = ninf, bv3 = ninf;
+              int bi0 = 0, bi1 = 0, bi2 = 0, bi3 = 0;
+#pragma unroll
+              for (int c4 = 0; c4 < kVB; c4 += 4) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
+                float x;
+                x = a4.x + ecol[c4 + 0]; if (x >= bv0) { bv0 = x; bi0 = c4 + 0; }
+                x = a4.y + ecol[c4 + 1]; if (x >= bv1) { bv1 = x; bi1 = c4 + 1; }
+                x = a4.z + ecol[c4 + 2]; if (x >= bv2) { bv2 = x; bi2 = c4 + 2; }
+                x = a4.w + ecol[c4 + 3]; if (x >= bv3) { bv3 = x; bi3 = c4 + 3; }
+              }
+              const float bvs[4] = {bv0, bv1, bv2, bv3};
+              const int bis[4] = {bi0, bi1, bi2, bi3};
+              float nv = ninf; int ni = 0;
+#pragma unroll
+              for (int r4 = 0; r4 < 4; r4++) {
+                const int u = ord[r4];
+                const float v = (u == 0) ? bvs[0] : (u == 1) ? bvs[1] : (u == 2) ? bvs[2] : bvs[3];
+                const int ii = (u == 0) ? bis[0] : (u == 1) ? bis[1] : (u == 2) ? bis[2] : bis[3];
+                if (r4 == 0 || v > nv) { nv = v; ni = ii; }
+              }
+              const int nd = dbase - ni;
+              const float rv = xvw[rr * kV2Pitch];
+              const int rd = xdw[rr * kV2Pitch];
+              if (nv > rv || (nv == rv && nv > ninf && rank4(nd) <= rank4(rd))) {
+                xvw[rr * kV2Pitch] = nv;
+                xdw[rr * kV2Pitch] = nd;
+              }
+            }
+          }
+          asm volatile("cp.async.wait_all;" ::: "memory");
+        }
+      }
+      __syncthreads();
+      // ======================= chain phase: lanes = rows, serial over the 32 columns =======================
+      {
+        const int ts = warp >> 2;
+        const int c = cb + 2 * ts;
+        if (c <= c_hi && (warp & 3) == (ts & 3)) {
+          const int J = w - c;
+          const int jbase = kVB * J;
+          const int s = c * kVB + lane;
+          const bool rowvalid = s < nsteps;
+          const int t = 1 + s;
+          const float *edw = s_ed + (size_t)ts * kVB * kVB;
+          float *iow = s_io + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          const float *xvw = s_xv + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          int *xdw = s_xd + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          float d0v = ninf; int d0d = 0;
+          {
+            const int tp = c * kVB;   // previous-row index of the chunk's first row (written by the other CTA)
+            const float pv = (jbase + lane < L) ? __ldcg(lat + (int64_t)tp * L + jbase + lane) : ninf;
+            for (int c4 = 0; c4 < kVB; c4 += 4) {
+              const float4 e4 = *reinterpret_cast<const float4 *>(edw + lane * kVB + c4);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int ci = c4 + k;
+                const float x = __shfl_sync(0xffffffffu, pv, ci) + (k == 0 ? e4.x : k == 1 ? e4.y : k == 2 ? e4.z : e4.w);
+                const int delta = lane - ci;
+                if (ci < lane && better(x, delta, d0v, d0d)) { d0v = x; d0d = delta; }
+              }
+            }
+          }
+          float vrow[kVB];
+          bool anyfin = false;
+          vit_group<0>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vit_group<8>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vit_group<16>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vit_group<24>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          if (rowvalid) flag[t * NB + J] = anyfin ? 1 : 0;
+          __syncwarp();
+          const int rl = min(kVB, nsteps - c * kVB) - 1;
+          const float *iot = s_io + (size_t)ts * kVB * kV2Pitch;
+          const int *trt = s_xd + (size_t)ts * kVB * kV2Pitch;
+          const int j = jbase + lane;
+          if (j < L) {
+            for (int rr = 0; rr <= rl; rr++) {
+              const int64_t off = (int64_t)(1 + c * kVB + rr) * L + j;
+              lat[off] = iot[rr * kV2Pitch + lane];
+              trg[off] = (uint16_t)trt[rr * kV2Pitch + lane];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    cluster_sync_all();    // wave w is complete in both CTAs and visible to both
+  }
+
+  // backtrace (dag_best_alignment.cu:178-184)
+  if (rank == 0 && threadIdx.x == 0) {
+    int code = DAGB200_ST_OK;
+    if (!(__ldcg(lat + (int64_t)(Tn - 1) * L + O - 1) > ninf)) {
+      code = DAGB200_ST_NO_PATH;
+    } else {
+      int pos = O - 1;
+      for (int i = Tn - 1; i >= 0; i--) {
+        prow[pos] = i;
+        if (i == 0) break;
+        const int d = __ldcg(trg + (int64_t)i * L + pos);
+        if (d == 0) { code = DAGB200_ST_NO_PATH; break; }
+        pos -= d;
+      }
+    }
+    if (status) status[b] = code;
+  }
+}
+
+size_t vitc_smem_bytes() {
+  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 3 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * 8 * kVB) + 16;
+}
+
 size_t vit2_smem_bytes(int M, int L) {
   const int NB = (L + kVB - 1) / kVB;
   return sizeof(float) * ((size_t)kV2Tpw * kVB * kVB + 3 * (size_t)kV2Tpw * kVB * kV2Pitch + (size_t)kV2Warps * 16 * kVB) +
@@ -351,9 +595,20 @@ size_t vit2_smem_bytes(int M, int L) {
 bool vit2_supported(int M, int L) { return vit2_smem_bytes(M, L) <= 200 * 1024; }
 
 int launch_viterbi_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
-                           float *lattice, uint16_t *trace, int32_t *path, int B, int M, int L, int Tl,
-                           int32_t *status, cudaStream_t st) {
+                           float *lattice, uint16_t *trace, int32_t *path, unsigned char *flags, int B, int M, int L,
+                           int Tl, int32_t *status, cudaStream_t st) {
   const int NB = (L + kVB - 1) / kVB;
+  static const int vit_version = getenv("DAGB200_VIT") ? atoi(getenv("DAGB200_VIT")) : 3;
+  if (vit_version >= 3 && flags && 2 * (int64_t)B <= 2147483647) {
+    const size_t smemc = vitc_smem_bytes();
+    cudaFuncSetAttribute(dag_viterbi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc);
+    prof_mark(6, st);
+    dag_viterbi_cluster_kernel<<<2 * B, kV2Threads, smemc, st>>>(match, links, olen, tlen, lattice, trace, path, flags, M, L,
+                                                                Tl, NB, status);
+    DAGB200_CHECK_LAUNCH("dag_viterbi_cluster_kernel");
+    prof_mark(7, st);
+    return 0;
+  }
   const size_t smem = vit2_smem_bytes(M, L);
   cudaFuncSetAttribute(dag_viterbi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   prof_mark(6, st);
