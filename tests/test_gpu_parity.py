@@ -111,6 +111,9 @@ SHAPES = [
     (2, 1100, 24, 1099, True, 0.0),  # L > block size (strided sweep)
     (5, 257, 64, 64, True, 0.25),    # GLAT force-emit 0 / -inf emissions
     (67, 96, 20, 95, True, 0.0),     # many samples
+    (2, 352, 300, 351, True, 0.0),   # more than 256 target rows: two passes of the column-major recurrences
+    (1, 640, 530, 639, False, 0.0),  # three passes, 17 row chunks (odd split between the Viterbi cluster CTAs)
+    (2, 320, 290, 40, True, 0.1),    # two passes, banded transitions, forced emissions
 ]
 
 
@@ -125,10 +128,18 @@ def test_dag_loss_against_oracle(shape):
     fin = np.isfinite(ol64)
     assert np.array_equal(np.isfinite(loss), fin)
     assert np.allclose(loss[fin], ol64[fin], rtol=1e-4, atol=0)
-    gof = np.where(fin, go, 0)[:, None, None]
-    assert relerr(gm, np.where(fin[:, None, None], ogm, 0)) <= 1e-4
-    assert relerr(gl, np.where(fin[:, None, None], ogl, 0)) <= 1e-4
-    del gof
+    tol_m = tol_l = 1e-4
+    if M > 128:
+        # lattice values ~1e3 carry an fp32 ulp of 6e-5..1.2e-4: the reference's own fp32 arithmetic (restated in the
+        # oracle's fp32 build) is then only accurate to ~1e-4, so the bar is relative to it (DESIGN.md "Numerics")
+        _, a32, b32 = oracle.dag_loss(match, links, olen, tlen, True, np.float32)
+        gm32, gl32 = oracle.dag_loss_backward(go, a32, b32, match, links, olen, tlen, np.float32)
+        tol_m = max(1e-4, 1.5 * relerr(np.where(fin[:, None, None], gm32, 0), np.where(fin[:, None, None], ogm, 0)))
+        tol_l = max(1e-4, 1.5 * relerr(np.where(fin[:, None, None], gl32, 0), np.where(fin[:, None, None], ogl, 0)))
+    em, el = relerr(gm, np.where(fin[:, None, None], ogm, 0)), relerr(gl, np.where(fin[:, None, None], ogl, 0))
+    print("grad errors", em, el, "tolerances", tol_m, tol_l)
+    assert em <= tol_m
+    assert el <= tol_l
     check_lattice_side_outputs(alpha.cpu().numpy(), beta.cpu().numpy(), oa, ob, match, ol64)
 
 
