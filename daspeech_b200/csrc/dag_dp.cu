@@ -374,6 +374,10 @@ size_t dp2_workspace_bytes(int B, int M, int L);
 bool dp2_supported(int M, int L);
 extern int g_exact_mode;
 bool dp3_supported(int M, int L);
+bool dp4_supported(int M, int L);
+int launch_alpha_beta_tcgen05(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
+                              float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
+                              int32_t *status, cudaStream_t st);
 int launch_alpha_beta_colmajor(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                                float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
                                int32_t *status, cudaStream_t st);
@@ -405,7 +409,11 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
     cudaError_t e = cudaMemsetAsync(beta, 0, (size_t)B * M * L * esz, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(beta)");
   }
-  static const int dp_version = getenv("DAGB200_DP") ? atoi(getenv("DAGB200_DP")) : 3;
+  static const int dp_version = getenv("DAGB200_DP") ? atoi(getenv("DAGB200_DP")) : 4;
+  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp_version >= 4 && dp4_supported(M, L) &&
+      workspace_bytes >= dp2_workspace_bytes(B, M, L))
+    return launch_alpha_beta_tcgen05((const float *)match, (const float *)links, output_length, target_length,
+                                     (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
   if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp_version >= 3 && dp3_supported(M, L) &&
       workspace_bytes >= dp2_workspace_bytes(B, M, L))
     return launch_alpha_beta_colmajor((const float *)match, (const float *)links, output_length, target_length,

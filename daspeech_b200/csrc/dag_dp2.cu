@@ -639,7 +639,8 @@ size_t dp2_smem_bytes(int M, int L) {
                           2 * (size_t)lay.NB * kBlk + (size_t)lay.NB * 4 + (size_t)M * lay.NB);
 }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, cudaStream_t st);
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, int fmt,
+                    cudaStream_t st);
 
 size_t dp2_workspace_bytes(int B, int M, int L) { return TileLayout::make(L, M).sample_bytes * (size_t)B; }
 
@@ -649,7 +650,7 @@ int launch_alpha_beta_blocked(const float *match, const float *links, const int6
                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
                               int32_t *status, cudaStream_t st) {
   prof_mark(0, st);
-  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, st);
+  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, 0, st);
   if (rc) return rc;
   prof_mark(1, st);
   TileLayout lay = TileLayout::make(L, M);

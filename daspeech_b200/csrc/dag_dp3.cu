@@ -848,14 +848,15 @@ size_t dp3_smem_bytes(int M, int L) {
 
 bool dp3_supported(int M, int L) { return L >= 1 && M >= 2 && dp3_smem_bytes(M, L) <= 227 * 1024; }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, cudaStream_t st);
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, int fmt,
+                    cudaStream_t st);
 
 int launch_alpha_beta_colmajor(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                                float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
                                int32_t *status, cudaStream_t st) {
   using namespace dp3;
   prof_mark(0, st);
-  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, st);
+  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, 0, st);
   if (rc) return rc;
   prof_mark(1, st);
   TileLayout lay = TileLayout::make(L, M);

@@ -51,7 +51,7 @@ dag_rowmax_kernel(const float *__restrict__ links, const int64_t *__restrict__ o
 // pass 2: one CTA (4 warps) per 32x32 tile (I <= J): P' = exp(links - rmax) into the operand layouts
 __global__ void __launch_bounds__(128)
 dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ olen, unsigned char *__restrict__ ws,
-                 int L, int Tl, TileLayout lay) {
+                 int L, int Tl, TileLayout lay, int fmt) {
   __shared__ float tile[kBlk][kBlk + 1];
   const int I = blockIdx.y, b = blockIdx.z;
   const int J = I + blockIdx.x;                    // blockIdx.x = block distance, 0 .. band
@@ -93,6 +93,27 @@ dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ ol
       pA[r * kBlk + lane] = (double)tile[r][lane];                            // P'[ci][cj]
       pB[r * kBlk + lane] = (double)tile[kBlk - 1 - lane][kBlk - 1 - r];      // P'[31-cj][31-ci]
     }
+  } else if (fmt == 1) {
+    // canonical K-major core-matrix layout of tcgen05 (dag_dp4.cu): [plane hi|lo][k-core][n = 32][8 bf16 along K];
+    // alpha direction: K = source, N = destination; beta direction: K = destination, N = source
+    uint4 *tA = reinterpret_cast<uint4 *>(base + lay.off_tilesA + lay.idxA(I, J) * kTileBytes);
+    uint4 *tB = reinterpret_cast<uint4 *>(base + lay.off_tilesB + lay.idxB(I, J) * kTileBytes);
+    for (int x = threadIdx.x; x < 128; x += 128) {
+      const int kc = x >> 5, n = x & 31;
+      float a[8], bq[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) { a[e] = tile[8 * kc + e][n]; bq[e] = tile[n][8 * kc + e]; }
+      uint4 ha, la, hb, lb;
+      auto split2 = [](float x0, float x1, uint32_t &h, uint32_t &l) {
+        const float h0 = bf16_hi_part(x0), h1 = bf16_hi_part(x1);
+        h = pack_bf16_pair(h0, h1);
+        l = pack_bf16_pair(x0 - h0, x1 - h1);
+      };
+      split2(a[0], a[1], ha.x, la.x); split2(a[2], a[3], ha.y, la.y); split2(a[4], a[5], ha.z, la.z); split2(a[6], a[7], ha.w, la.w);
+      split2(bq[0], bq[1], hb.x, lb.x); split2(bq[2], bq[3], hb.y, lb.y); split2(bq[4], bq[5], hb.z, lb.z); split2(bq[6], bq[7], hb.w, lb.w);
+      tA[kc * 32 + n] = ha; tA[128 + kc * 32 + n] = la;
+      tB[kc * 32 + n] = hb; tB[128 + kc * 32 + n] = lb;
+    }
   } else {
     uint4 *tA = reinterpret_cast<uint4 *>(base + lay.off_tilesA + lay.idxA(I, J) * kTileBytes);
     uint4 *tB = reinterpret_cast<uint4 *>(base + lay.off_tilesB + lay.idxB(I, J) * kTileBytes);
@@ -120,7 +141,8 @@ dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ ol
   }
 }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, cudaStream_t st) {
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, int fmt,
+                    cudaStream_t st) {
   TileLayout lay = TileLayout::make(L, M);
   {
     dim3 grid((lay.NB * kBlk + 7) / 8, B);
@@ -130,7 +152,7 @@ int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, in
   {
     const int nd = min(lay.NB, band_blocks(Tl) + 1);
     dim3 grid(nd, lay.NB, B);
-    dag_tiles_kernel<<<grid, 128, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay);
+    dag_tiles_kernel<<<grid, 128, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay, fmt);
     DAGB200_CHECK_LAUNCH("dag_tiles_kernel");
   }
   return 0;

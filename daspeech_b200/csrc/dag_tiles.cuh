@@ -37,6 +37,10 @@ struct TileLayout {
   // computed column ci for the later column cj) and the row handed from the last chunk of a pass to the first
   // chunk of the next one: [2 (pass parity)][NB][32] fp64 predecessor sums + [2][NB] integer anchors
   size_t off_pushA, off_pushB, off_passA, off_passB, off_passfA, off_passfB;
+  // tcgen05 kernel (dag_dp4.cu): previous-row masses as the A operand in the canonical K-major core-matrix layout:
+  // [2 planes (bf16 hi, lo)][NB*4 k-cores of 8 vertices (sweep order)][Mr consumer rows][16 bytes]
+  int Mr;
+  size_t off_aopA, off_aopB;
   __host__ __device__ static inline TileLayout make(int L, int M = 2) {
     TileLayout t;
     t.NB = (L + kBlk - 1) / kBlk;
@@ -59,6 +63,10 @@ struct TileLayout {
     t.off_passB = o;  o += (size_t)2 * t.NB * kBlk * sizeof(double);
     t.off_passfA = o; o += (((size_t)2 * t.NB * sizeof(int)) + 255) & ~(size_t)255;
     t.off_passfB = o; o += (((size_t)2 * t.NB * sizeof(int)) + 255) & ~(size_t)255;
+    o = (o + 255) & ~(size_t)255;
+    t.Mr = ((t.NC + 7) / 8) * 256;
+    t.off_aopA = o;   o += (size_t)2 * t.NB * 4 * t.Mr * 16;
+    t.off_aopB = o;   o += (size_t)2 * t.NB * 4 * t.Mr * 16;
     t.sample_bytes = (o + 255) & ~(size_t)255;
     return t;
   }
