@@ -312,14 +312,14 @@ def main():
         for i in range(5):
             prof[i] += max(buf[i], 0.0) / kp
     lib.dagb200_set_profile(0)
-    kern = {"dag_rowmax_kernel+dag_tiles_kernel": prof[0], "dag_alpha_beta_colmajor_kernel": prof[1],
+    kern = {"dag_rowmax_kernel+dag_tiles_kernel": prof[0], "dag_alpha_beta_tcgen05_kernel": prof[1],
             "grad_planes_kernel": prof[2], "grad_links_planes_kernel": prof[3]}
     # algorithmic bytes of the launch each kernel belongs to: the forward pair
     # (precompute + recurrences) moves 4(3N+E), the backward pair 4(4N+2E)
     N_, E_ = B * M * L, B * L * T
-    kbytes = {"dag_alpha_beta_colmajor_kernel": bytes_["fwd"], "grad_links_planes_kernel": 4 * (2 * N_ + 2 * E_),
+    kbytes = {"dag_alpha_beta_tcgen05_kernel": bytes_["fwd"], "grad_links_planes_kernel": 4 * (2 * N_ + 2 * E_),
               "dag_rowmax_kernel+dag_tiles_kernel": 4 * E_, "grad_planes_kernel": 4 * 4 * N_}
-    dom_name = max(("dag_alpha_beta_colmajor_kernel", "grad_links_planes_kernel"), key=lambda n: kern[n])
+    dom_name = max(("dag_alpha_beta_tcgen05_kernel", "grad_links_planes_kernel"), key=lambda n: kern[n])
     fwd_ms = prof[0] + prof[1]
     bwd_ms = prof[2] + prof[3]
     dom_ms = kern[dom_name]
