@@ -30,6 +30,7 @@ constexpr int kThreads = 576;                  // 8 chain warps + 8 epilogue war
 constexpr int kCW = 8;                          // chain warps = chunks per pass (GEMM warps: the other 8)
 constexpr int kStages = 3;                      // operand ring: {A slab 16 KB, transition tile 4 KB}
 constexpr int kStageBytes = 20480;
+constexpr int kTSlots = 16;                     // TMEM accumulator slots of 32 columns (all 512 columns)
 constexpr int kIssuerWarp = 16;
 constexpr int kProducerWarp = 17;
 constexpr int kPitch = 33;                      // padded row pitch of 32x32 fp32 tiles in shared memory
@@ -150,26 +151,28 @@ struct Smem {
   unsigned char *ring;  // [kStages][kStageBytes] operand ring: A slab [2 planes][4 k-cores][128 rows][16 B], then the
                         //                        transition tile [2 planes][4 k-cores][32 vertices][16 B]
   unsigned char *afresh;// [2 planes][4 k-cores][256 rows][16 B]  the block just finished, as the A operand of phase 2
-  double *ut;       // [2][32*32]          fp64 push table of the current / next block
+  double *ut;       // [32*32]             fp64 push table of the current block
   float *xbuf;      // [kCW][kTileF]       far sums in -> masses out (normalised fp32 after phase 1)
-  float *io;        // [kCW][kTileF]       emissions in -> lattice values out
+  float *io;        // [2][kCW][kTileF]    emission weights in (high words of fp64) -> incoming masses out (high words);
+                    //                     written / drained by the epilogue warps one block ahead / behind the chain
+  float *rmxs;      // [2][kCW][32]        per-column transition maximum folded into the emission weights (alpha: 0 where a vertex has no successor)
   double *hand;     // [kCW][32]           predecessor sums of a chunk's last row, handed to the next chunk
   int *fbuf;        // [kCW][32]           far frames of the rows of the current tile
   int *prog;        // [kCW]               progress counters of the chain warps (events)
   int *tanchor;     // [kCW]               fp64 frame of each chain warp's current tile
-  float *rmax;      // [NB*32]             per-source-vertex transition maximum
-  int *rmtab;       // [257][NB]           per (row of the pass, block) integer upper bound of log2(outgoing mass)
+  short *rmtab;     // [257][NB]           per (row of the pass, block) integer upper bound of log2(outgoing mass)
   uint64_t *full;   // [kStages]           ring stage filled (TMA)
   uint64_t *empty;  // [kStages]           ring stage consumed (tcgen05.commit)
-  uint64_t *tfull;  // [2]                 TMEM accumulator slot written (tcgen05.commit)
-  uint64_t *tempty; // [2]                 TMEM accumulator slot read back (4 epilogue warps)
-  uint64_t *ubar;   // [2]
+  uint64_t *tfull;  // [kTSlots]           TMEM accumulator slot written (tcgen05.commit)
+  uint64_t *tempty; // [kTSlots]           TMEM accumulator slot read back (4 epilogue warps)
+  uint64_t *ubar;   // [1]
   uint32_t *tmem;   // TMEM base address
 };
 
 struct Geo {
   int O, Tn, M, L, NB, NBv, nsteps, NCv, NP, band, Mr;
   bool dbg;
+  int dbgmode;
 };
 
 // a tile without a single lattice cell (below the diagonal j >= t): nothing flows through it
@@ -180,6 +183,57 @@ __device__ __forceinline__ bool tile_geo_dead(const Geo &g, int c, int J) {
   return min(kBlk * J + 31, g.O - 1) < tmin;
 }
 
+// frames are stored as int16 (|frame| < 32767 covers lattice values down to -22 000 nats); -32768 = no mass
+__device__ __forceinline__ void rm_store(short *p, int v) { *p = (short)(v <= kNegBig ? -32768 : max(min(v, 32767), -32767)); }
+__device__ __forceinline__ int rm_load(const short *p) { const int v = *p; return v == -32768 ? kNegBig : v; }
+
+// high word of the fp64 emission weight exp(em + rmx) (21 significant bits; 0 when it vanishes)
+__device__ __forceinline__ int ew_word(float em, float rmx) {
+  const float w2 = (em + rmx) * kLog2e;
+  int word = 0;
+  if (w2 > -1.0e30f) {
+    const float wf = floorf(w2);
+    const int fb = __float_as_int(exp2f(w2 - wf));            // [1, 2]
+    const int iw = (int)wf + ((fb >> 23) - 127);
+    if (iw > -1023 && iw < 1024) word = ((iw + 1023) << 20) | ((fb & 0x7fffff) >> 3);
+  }
+  return word;
+}
+
+// ---- epilogue-warp side jobs (lanes = columns): emission weights of a block BEFORE the chain warps reach it, lattice
+// values of a block AFTER they left it.  Both touch global memory, off the chain warps' critical path.
+template <bool BETA>
+__device__ __forceinline__ void epi_prepass(const Geo &g, const Smem &sm, const float *__restrict__ match,
+                                            const float *__restrict__ g_rmax, int p, int qn, int ew, int lane) {
+  const int c = p * kCW + ew;
+  const int Jn = BETA ? g.NBv - 1 - qn : qn;
+  const int jn = kBlk * Jn + lane;
+  float *iot = sm.io + ((size_t)(qn & 1) * kCW + ew) * kTileF;
+  float rmxn = jn < g.O ? __ldg(g_rmax + jn) : neg_inf_f();
+  // alpha masses carry exp(rmax) of their own vertex; a vertex without successors (rmax = -inf) still has a forward
+  // value and its mass meets only zero transitions, so its weight is taken without the factor
+  if (!BETA && jn < g.O && rmxn == neg_inf_f()) rmxn = 0.f;
+  sm.rmxs[((qn & 1) * kCW + ew) * 32 + lane] = rmxn;
+  const int jc = min(jn, g.L - 1);
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {          // two batches of 16 independent loads
+    float em[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      const int sr = c * 32 + 16 * h + r;
+      const int tr = min(max(BETA ? g.Tn - 2 - sr : 1 + sr, 0), g.M - 1);
+      em[r] = __ldg(match + (int64_t)tr * g.L + jc);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      const int rr = 16 * h + r, sr = c * 32 + rr;
+      const int tr = BETA ? g.Tn - 2 - sr : 1 + sr;
+      int word = 0;
+      if (sr < g.nsteps && jn >= tr && jn < g.O) word = ew_word(em[r], rmxn);
+      iot[rr * kPitch + lane] = __int_as_float(word);
+    }
+  }
+}
 // The row of block q that lane `lane` of chain warp cw just finished (normalised masses v[0..31], K index = vertex
 // offset) becomes consumer row cr = 32 cw + lane + 1 of the pass: bf16 hi/lo, 16 bytes per 8-vertex core, into the
 // shared-memory operand of phase 2 (rows < 256) and into the global operand store (all later destination blocks).
@@ -221,21 +275,12 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   const bool rowvalid = s < g.nsteps;
   const int t = BETA ? g.Tn - 2 - s : 1 + s;
   float *xb = sm.xbuf + (size_t)cw * kTileF;
-  float *iob = sm.io + (size_t)cw * kTileF;
+  float *iob = sm.io + ((size_t)(q & 1) * kCW + cw) * kTileF;
   float *mrow = xb + lane * kPitch;
   float *iow = iob + lane * kPitch;
   const float ninf = neg_inf_f();
   const bool feeds_next = (c + 1 < g.NCv);       // somebody consumes my last row
   const bool to_pass = feeds_next && cw == kCW - 1;
-
-  // (1) pull the emission rows of the next block towards L2 (they are staged in phase 2, after this block's lattice
-  // values have left the buffer)
-  if (q + 1 < g.NBv) {
-    const int Jn = BETA ? g.NBv - 2 - q : q + 1;
-    const int sr = c * 32 + lane;
-    const int tr = BETA ? g.Tn - 2 - sr : 1 + sr;
-    if (sr < g.nsteps && kBlk * Jn < g.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(match + (int64_t)tr * g.L + kBlk * Jn));
-  }
 
   // (2) frames: far frames of my rows, the frame handed from the chunk above, the fp64 frame of this tile
   const int FI = sm.fbuf[cw * 32 + lane];
@@ -263,24 +308,21 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
     if (lane == 0) passf[((p + 1) & 1) * g.NB + q] = Ft;
     if (dead) passd[((size_t)((p + 1) & 1) * g.NB + q) * 32 + lane] = 0.0;
   }
-  // emissions of THIS block have landed (staged in phase 2 of the previous block / the pass prologue)
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
   if (dead) {   // nothing reaches this tile: -inf lattice values, zero masses
 #pragma unroll 4
-    for (int k = 0; k < 32; k++) { iow[k] = ninf; mrow[k] = 0.f; }
-    sm.rmtab[(cw * 32 + lane + 1) * g.NB + q] = kNegBig;
+    for (int k = 0; k < 32; k++) { iow[k] = neg_inf_f(); mrow[k] = 0.f; }
+    rm_store(sm.rmtab + (cw * 32 + lane + 1) * g.NB + q, kNegBig);
     publish_row(g, sm, aop, mrow, p, q, cw, lane, true);
     proxy_fence_async();
     __syncwarp();
     return;
   }
   // (3) the fp64 push table of this block
-  mbar_wait(sm.ubar + (ustep & 1), (ustep >> 1) & 1);
-  const double *ut = sm.ut + (size_t)(ustep & 1) * 1024;
+  mbar_wait(sm.ubar, ustep & 1);
+  const double *ut = sm.ut;
   const double hs = pow2d(Fh - Ft);              // handed sums are in the frame of the tile above
   const double xs = pow2d(FI - Ft);              // far sums of my row are in the frame FI
-  const float *rmax_blk = sm.rmax + jbase;
   int maxhi = 0;
 
   // (4) column sweep: four groups of 8 columns (runtime loop keeps the code small)
@@ -304,8 +346,6 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
     for (int K = 0; K < 8; K++) {
       const int cj = 8 * G + K;
       const int jj = BETA ? 31 - cj : cj;
-      const int j = jbase + jj;
-      const bool valid = rowvalid && j >= t && j < g.O;
       // what the row above hands to this column (lane 0: from the chunk above / the previous pass)
       double z;
       if (cw == 0) {
@@ -325,32 +365,10 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
       }
       double rm = __shfl_up_sync(0xffffffffu, a[K], 1);
       if (lane == 0) rm = z;
-      const float X = mrow[jj];
-      const double tot = fma((double)X, xs, rm);
-      // emission weight exp(match + rmax) as a double (0 for cells outside the lattice)
-      const float em = iow[jj];
-      const float rmx = rmax_blk[jj];
-      const float w2 = (em + rmx) * kLog2e;
-      double ewd = 0.0;
-      if (valid && w2 > -1.0e30f) {
-        const float wf = floorf(w2);
-        ewd = (double)exp2f(w2 - wf) * pow2d((int)wf);
-      }
-      const double m = tot * ewd;
-      // lattice value (off the dependency path): log of tot through its exponent and leading mantissa bits
-      float out = ninf;
-      const int thi = __double2hiint(tot);
-      if (valid && thi >= 0x00100000) {
-        const int tlo = __double2loint(tot);
-        const int e2 = (thi >> 20) - 1023 + Ft;
-        const float mant = __int_as_float(0x3f800000 | ((thi & 0xfffff) << 3) | ((unsigned)tlo >> 29));
-        const float fl = (float)e2;
-        out = (em + fmaf(__log2f(mant), 0.6931471805599453f, fl * kLn2Lo)) + fl * kLn2Hi;
-        if (BETA) out += rmx;
-      }
-      iow[jj] = out;
+      const double tot = fma((double)mrow[jj], xs, rm);
+      const double m = tot * __hiloint2double(__float_as_int(iow[jj]), 0);   // emission weight: 0 outside the lattice
       const int mhi = __double2hiint(m);
-      mrow[jj] = __int_as_float(mhi);             // mass, 21 significant bits, frame Ft
+      mrow[jj] = __int_as_float(mhi);                  // outgoing mass, 21 significant bits, frame Ft
       maxhi = max(maxhi, mhi);
       // push into the later columns of my row
       if (K < 7) {
@@ -364,11 +382,20 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   // (5) row frame and normalised masses (value / 2^maxe < 1) for the A-operand fragments
   const int emf = maxhi >> 20;                   // biased exponent of the largest mass of my row (0: none)
   const int maxe = (emf > 0) ? Ft + emf - 1022 : kNegBig;
-  sm.rmtab[(cw * 32 + lane + 1) * g.NB + q] = maxe;
+  rm_store(sm.rmtab + (cw * 32 + lane + 1) * g.NB + q, maxe);
+  const float *rmxw = sm.rmxs + ((q & 1) * kCW + cw) * 32;
 #pragma unroll 8
   for (int k = 0; k < 32; k++) {
     const int w = __float_as_int(mrow[k]);
     const int we = w >> 20;
+    // lattice value = log(outgoing mass) - rmax (alpha) / log(outgoing mass) (beta), off the dependency path
+    float out = neg_inf_f();
+    if (we > 0) {
+      const float fl = (float)(we - 1023 + Ft);
+      out = fmaf(__log2f(__int_as_float(0x3f800000 | ((w & 0xfffff) << 3))), 0.6931471805599453f, fl * kLn2Lo) + fl * kLn2Hi;
+      if (!BETA) out -= rmxw[k];
+    }
+    iow[k] = out;
     const int fe = we - emf + 126;
     const int bits = (we > 0 && fe > 0) ? ((fe << 23) | ((w & 0xfffff) << 3)) : 0;
     mrow[k] = __int_as_float(bits);
@@ -379,36 +406,23 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   __syncwarp();
 }
 
-// phase 2 of a chain warp: write the lattice rows of this block, stage the emissions of the next one
+// phase 2 of a chain warp: the lattice rows of the block (lanes = columns, coalesced)
 template <bool BETA>
-__device__ __forceinline__ void chain_phase2(const Geo &g, const Smem &sm, const float *__restrict__ match,
-                                             float *__restrict__ lat, int p, int q, int cw, int lane) {
+__device__ __forceinline__ void chain_phase2(const Geo &g, const Smem &sm, float *__restrict__ lat, int p, int q, int cw,
+                                             int lane) {
   const int c = p * kCW + cw;
   const int J = BETA ? g.NBv - 1 - q : q;
-  float *iot = sm.io + (size_t)cw * kTileF;
-  const float ninf = neg_inf_f();
-  // lattice values: coalesced row writes (lane = column)
+  const float *iot = sm.io + ((size_t)(q & 1) * kCW + cw) * kTileF;
   const int j = kBlk * J + lane;
   const int rl = min(32, g.nsteps - c * 32) - 1;
   if (j < g.L) {
+#pragma unroll 4
     for (int rr = 0; rr <= rl; rr++) {
       const int sr = c * 32 + rr;
       const int tr = BETA ? g.Tn - 2 - sr : 1 + sr;
       lat[(int64_t)tr * g.L + j] = iot[rr * kPitch + lane];
     }
   }
-  __syncwarp();
-  if (q + 1 < g.NBv) {
-    const int Jn = BETA ? g.NBv - 2 - q : q + 1;
-    const int jn = kBlk * Jn + lane;
-    for (int rr = 0; rr < 32; rr++) {
-      const int sr = c * 32 + rr;
-      const int tr = BETA ? g.Tn - 2 - sr : 1 + sr;
-      if (sr < g.nsteps && jn < g.L) cp_async_f32(iot + rr * kPitch + lane, match + (int64_t)tr * g.L + jn);
-      else iot[rr * kPitch + lane] = ninf;
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -470,7 +484,7 @@ struct Issuer {
 };
 __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t tmem_base, uint32_t ring_u32, uint32_t afresh_u32,
                                            bool from_afresh, int mt) {
-  const int st = is.n % kStages, pp = is.n & 1, k = is.n >> 1;
+  const int st = is.n % kStages, pp = is.n % kTSlots, k = is.n / kTSlots;
   long long c0 = is.dbg ? clock64() : 0;
   mbar_wait(sm.full + st, (is.n / kStages) & 1);
   long long c1 = is.dbg ? clock64() : 0;
@@ -509,7 +523,7 @@ struct Epi {
 
 // take one item: wait for its accumulator, read my row, release the slot, add with the power-of-two scale
 __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_base, int quarter, int Fs, bool mine) {
-  const int pp = e.n & 1, k = e.n >> 1;
+  const int pp = e.n % kTSlots, k = e.n / kTSlots;
   e.n++;
   if (!mine) return;
   mbar_wait(sm.tfull + pp, k & 1);
@@ -536,7 +550,8 @@ __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_b
 // One direction of one utterance.
 template <bool BETA>
 __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict__ lat, unsigned char *__restrict__ ws,
-                             const TileLayout &lay, const Smem &sm, int O, int Tn, int M, int L, int Tl, bool dbg) {
+                             const TileLayout &lay, const Smem &sm, int O, int Tn, int M, int L, int Tl, int dbgi) {
+  const bool dbg = dbgi != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float ninf = neg_inf_f();
   Geo g;
@@ -548,6 +563,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   g.band = band_blocks(Tl);
   g.Mr = lay.Mr;
   g.dbg = dbg;
+  g.dbgmode = dbgi;
   const float *g_rmax = reinterpret_cast<const float *>(ws + lay.off_rmax);
   const double *push = reinterpret_cast<const double *>(ws + (BETA ? lay.off_pushB : lay.off_pushA));
   const unsigned char *tiles = ws + (BETA ? lay.off_tilesB : lay.off_tilesA);
@@ -556,17 +572,17 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   int *passf = reinterpret_cast<int *>(ws + (BETA ? lay.off_passfB : lay.off_passfA));
 
   // ---- prologue ----------------------------------------------------------------------------------------
-  for (int x = threadIdx.x; x < g.NB * kBlk; x += kThreads) sm.rmax[x] = (x < O) ? g_rmax[x] : ninf;
-  for (int x = threadIdx.x; x < 257 * g.NB; x += kThreads) sm.rmtab[x] = kNegBig;
+  for (int x = threadIdx.x; x < 257 * g.NB; x += kThreads) sm.rmtab[x] = (short)-32768;
   for (int x = threadIdx.x; x < g.NB * 8; x += kThreads)               // consumer row 0 (the seed row): zeros
     *reinterpret_cast<uint4 *>(aop + (size_t)(x >> 3) * (g.Mr >> 7) * 16384 + (size_t)(x & 7) * 2048) = make_uint4(0u, 0u, 0u, 0u);
   for (int x = threadIdx.x; x < g.NB * 32; x += kThreads) passd[x] = 0.0;                             // parity 0
   for (int x = threadIdx.x; x < g.NB; x += kThreads) passf[x] = kNegBig;
   if (threadIdx.x < kStages) { mbar_init(sm.full + threadIdx.x, 1); mbar_init(sm.empty + threadIdx.x, 1); }
-  if (threadIdx.x < 2) { mbar_init(sm.ubar + threadIdx.x, 1); mbar_init(sm.tfull + threadIdx.x, 1); mbar_init(sm.tempty + threadIdx.x, 4); }
+  if (threadIdx.x < kTSlots) { mbar_init(sm.tfull + threadIdx.x, 1); mbar_init(sm.tempty + threadIdx.x, 4); }
+  if (threadIdx.x == 0) mbar_init(sm.ubar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   if (warp == kIssuerWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(sm.tmem)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(sm.tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   {
@@ -593,7 +609,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
     const int ci = BETA ? kBlk - 1 - jj : jj;
     const int q = BETA ? g.NBv - 1 - Jb : Jb;
     float v = match[(int64_t)seed_row * L + seed_col];
-    if (!BETA) v += sm.rmax[seed_col];   // alpha masses carry the best transition of their own vertex
+    if (!BETA) v += g_rmax[seed_col];    // alpha masses carry the best transition of their own vertex
     const float v2 = v * kLog2e;
     if (v2 > -1.0e30f) {
       const int F = (int)ceilf(v2);
@@ -601,7 +617,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
       passd[(size_t)q * 32 + lane] = (double)mant0 * push[((size_t)Jb * 32 + ci) * 32 + lane];
       if (lane == 0) {
         passf[q] = F;
-        sm.rmtab[0 * g.NB + q] = F + 1;
+        rm_store(sm.rmtab + q, F + 1);
         // consumer row 0 of block q: value mant0/2 in frame F+1 at K index = vertex offset jj
         const __nv_bfloat16 h = __float2bfloat16_rn(0.5f * mant0);
         const __nv_bfloat16 l = __float2bfloat16_rn(0.5f * mant0 - __bfloat162float(h));
@@ -631,28 +647,26 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
       const int ntl = (g.NCv - kCW * p > 4) ? 2 : 1;
       if (lane == 0 && p == 0) {
         const int J0 = BETA ? g.NBv - 1 : 0;
-        mbar_expect_tx(sm.ubar + 0, 8192);
-        bulk_g2s(sm.ut, push + (size_t)J0 * 1024, 8192, sm.ubar + 0);
+        mbar_expect_tx(sm.ubar, 8192);
+        bulk_g2s(sm.ut, push + (size_t)J0 * 1024, 8192, sm.ubar);
       }
       cta_sync();
       for (int q = 0; q < g.NBv; q++) {
-        const int ustep = p * g.NBv + q;
         const int J = q + 1;
         const bool have = J < g.NBv;
         if (lane == 0) {
-          if (have || p + 1 < g.NP) {   // push table of the next block
-            const int un = ustep + 1;
-            const int qn = have ? q + 1 : 0;
-            const int Jn = BETA ? g.NBv - 1 - qn : qn;
-            mbar_expect_tx(sm.ubar + (un & 1), 8192);
-            bulk_g2s(sm.ut + (size_t)(un & 1) * 1024, push + (size_t)Jn * 1024, 8192, sm.ubar + (un & 1));
-          }
           if (have) consumed += max(0, (J - 1) - max(0, J - g.band)) * ntl;
           producer_run<BETA>(pr, g, sm, aop, tiles, lay, p, q - 1, consumed + kStages);
         }
         __syncwarp();
         cta_sync();
         if (lane == 0) {
+          if (have || p + 1 < g.NP) {   // push table of the next block (the chain warps are done with this one)
+            const int qn = have ? q + 1 : 0;
+            const int Jn = BETA ? g.NBv - 1 - qn : qn;
+            mbar_expect_tx(sm.ubar, 8192);
+            bulk_g2s(sm.ut, push + (size_t)Jn * 1024, 8192, sm.ubar);
+          }
           if (have) consumed += ntl;
           producer_run<BETA>(pr, g, sm, aop, tiles, lay, p, q, consumed + kStages);
         }
@@ -699,6 +713,8 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
     const int mymt = ew >> 2, quarter = ew & 3;   // TMEM lanes 32 quarter .. (this warp's lane window: warp % 4)
     Epi e;
     e.n = 0;
+    const bool edbg = dbg && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 7);
+    long long t_post = 0, t_pre = 0, t_take = 0;
     const int et = threadIdx.x - kCW * 32;
     for (int p = 0; p < g.NP; p++) {
       const int ntl = (g.NCv - kCW * p > 4) ? 2 : 1;
@@ -714,10 +730,24 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
         for (int x = lane; x < kTileF; x += 32) xo[x] = 0.f;
         sm.fbuf[ew * 32 + lane] = kNegBig;
       }
+      if (active) epi_prepass<BETA>(g, sm, match, g_rmax, p, 0, ew, lane);   // emission weights of block 0
       cta_sync();
       for (int q = 0; q < g.NBv; q++) {
         const int J = q + 1;
         const bool have = J < g.NBv;
+        if (active && q + 2 < g.NBv) {   // pull the emission rows the next pre-pass reads towards L2
+          const int J2 = BETA ? g.NBv - 3 - q : q + 2;
+          const int sr = c * 32 + lane;
+          const int tr = BETA ? g.Tn - 2 - sr : 1 + sr;
+          if (sr < g.nsteps && kBlk * J2 < g.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(match + (int64_t)tr * g.L + kBlk * J2));
+        }
+        long long e0 = edbg ? clock64() : 0;
+        if (active) {   // lattice values of the block the chain warps just left, emission weights of the next one
+          long long e1 = edbg ? clock64() : 0;
+          if (have) epi_prepass<BETA>(g, sm, match, g_rmax, p, q + 1, ew, lane);
+          if (edbg) { t_post += e1 - e0; t_pre += clock64() - e1; }
+        }
+        long long e2 = edbg ? clock64() : 0;
         const bool tile_on = active && have && !tile_geo_dead<BETA>(g, c, BETA ? g.NBv - 1 - J : J);
         if (have) {
           // consumer row 0 of the pass (the last row of the previous pass / the seed) of block q for phase 2
@@ -733,15 +763,16 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
           for (int qs = max(0, J - g.band); qs <= J - 2; qs++)
             for (int mt = 0; mt < ntl; mt++) {
               const bool mine = (mt == mymt);
-              const int Fs = (mine && tile_on && rowvalid) ? sm.rmtab[(ew * 32 + lane) * g.NB + qs] : kNegBig;
+              const int Fs = (mine && tile_on && rowvalid) ? rm_load(sm.rmtab + (ew * 32 + lane) * g.NB + qs) : kNegBig;
               epi_take(e, sm, tmem_base, quarter, Fs, mine);
             }
         }
+        if (edbg) t_take += clock64() - e2;
         cta_sync();
         if (have) {
           for (int mt = 0; mt < ntl; mt++) {
             const bool mine = (mt == mymt);
-            const int Fs = (mine && tile_on && rowvalid) ? sm.rmtab[(ew * 32 + lane) * g.NB + (J - 1)] : kNegBig;
+            const int Fs = (mine && tile_on && rowvalid) ? rm_load(sm.rmtab + (ew * 32 + lane) * g.NB + (J - 1)) : kNegBig;
             epi_take(e, sm, tmem_base, quarter, Fs, mine);
           }
           if (active) {
@@ -754,23 +785,12 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
         cta_sync();
       }
     }
+    if (edbg) printf("[dp4 epilogue warp %d %s] post %lld  pre %lld  takes(phase 1) %lld\n", ew, BETA ? "beta" : "alpha", t_post, t_pre, t_take);
   } else {
     // ================================ chain warps ================================
     for (int p = 0; p < g.NP; p++) {
       const int c = p * kCW + cw;
       const bool active = c < g.NCv;
-      if (active) {     // emissions of block 0
-        const int J0 = BETA ? g.NBv - 1 : 0;
-        float *ion = sm.io + (size_t)cw * kTileF;
-        const int j = kBlk * J0 + lane;
-        for (int rr = 0; rr < 32; rr++) {
-          const int sr = c * 32 + rr;
-          const int tr = BETA ? Tn - 2 - sr : 1 + sr;
-          if (sr < g.nsteps && j < L) cp_async_f32(ion + rr * kPitch + lane, match + (int64_t)tr * L + j);
-          else ion[rr * kPitch + lane] = ninf;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
       cta_sync();
       for (int q = 0; q < g.NBv; q++) {
         const int ustep = p * g.NBv + q;
@@ -778,9 +798,8 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
         if (active) chain_phase1<BETA>(g, sm, match, passd, passf, aop, p, q, cw, lane, ustep);
         long long t1 = dbg ? clock64() : 0;
         cta_sync();
-        long long t2 = dbg ? clock64() : 0;
-        if (active) chain_phase2<BETA>(g, sm, match, lat, p, q, cw, lane);
-        if (dbg) { t_p1 += t1 - t0; t_p2 += clock64() - t2; }
+        if (active) chain_phase2<BETA>(g, sm, lat, p, q, cw, lane);
+        if (dbg) t_p1 += t1 - t0;
         cta_sync();
       }
     }
@@ -789,7 +808,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
     printf("[dp4 chain warp %d %s] phase1 %lld  phase2 %lld\n", warp, BETA ? "beta" : "alpha", t_p1, t_p2);
   tc_fence_before();
   __syncthreads();
-  if (warp == kIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+  if (warp == kIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -816,25 +835,25 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
   unsigned char *p = dp4_smem;
   sm.ring = p;                               p += (size_t)kStages * kStageBytes;
   sm.afresh = p;                             p += 32768;
-  sm.ut = reinterpret_cast<double *>(p);     p += 2 * 8192;
+  sm.ut = reinterpret_cast<double *>(p);     p += 8192;
   sm.hand = reinterpret_cast<double *>(p);   p += kCW * 32 * sizeof(double);
   sm.full = reinterpret_cast<uint64_t *>(p);   p += kStages * 8;
   sm.empty = reinterpret_cast<uint64_t *>(p);  p += kStages * 8;
-  sm.tfull = reinterpret_cast<uint64_t *>(p);  p += 2 * 8;
-  sm.tempty = reinterpret_cast<uint64_t *>(p); p += 2 * 8;
+  sm.tfull = reinterpret_cast<uint64_t *>(p);  p += kTSlots * 8;
+  sm.tempty = reinterpret_cast<uint64_t *>(p); p += kTSlots * 8;
   sm.ubar = reinterpret_cast<uint64_t *>(p);   p += 2 * 8;
   sm.tmem = reinterpret_cast<uint32_t *>(p);   p += 16;
   sm.xbuf = reinterpret_cast<float *>(p);    p += (size_t)kCW * kTileF * 4;
-  sm.io = reinterpret_cast<float *>(p);      p += (size_t)kCW * kTileF * 4;
+  sm.io = reinterpret_cast<float *>(p);      p += (size_t)2 * kCW * kTileF * 4;
+  sm.rmxs = reinterpret_cast<float *>(p);    p += 2 * kCW * 32 * 4;
   sm.fbuf = reinterpret_cast<int *>(p);      p += kCW * 32 * 4;
   sm.prog = reinterpret_cast<int *>(p);      p += kCW * 4;
   sm.tanchor = reinterpret_cast<int *>(p);   p += kCW * 4;
-  sm.rmax = reinterpret_cast<float *>(p);    p += (size_t)lay.NB * kBlk * 4;
-  sm.rmtab = reinterpret_cast<int *>(p);
+  sm.rmtab = reinterpret_cast<short *>(p);
   const float *m = match + b * latsz;
   unsigned char *wsb = ws + (size_t)b * lay.sample_bytes;
-  if (is_beta) colmajor_dir<true>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg != 0);
-  else colmajor_dir<false>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg != 0);
+  if (is_beta) colmajor_dir<true>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg);
+  else colmajor_dir<false>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg);
 }
 
 }  // namespace dp4
@@ -842,8 +861,8 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
 size_t dp4_smem_bytes(int M, int L) {
   using namespace dp4;
   TileLayout lay = TileLayout::make(L, M);
-  return (size_t)kStages * kStageBytes + 32768 + 2 * 8192 + kCW * 32 * 8 + (2 * kStages + 6) * 8 + 16 +
-         (size_t)2 * kCW * kTileF * 4 + kCW * 32 * 4 + 2 * kCW * 4 + (size_t)lay.NB * kBlk * 4 + (size_t)257 * lay.NB * 4;
+  return (size_t)kStages * kStageBytes + 32768 + 8192 + kCW * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 +
+         (size_t)3 * kCW * kTileF * 4 + 2 * kCW * 32 * 4 + kCW * 32 * 4 + 2 * kCW * 4 + (size_t)257 * lay.NB * 2 + 64;
 }
 
 bool dp4_supported(int M, int L) { return L >= 1 && M >= 2 && dp4_smem_bytes(M, L) <= 227 * 1024; }
@@ -862,10 +881,10 @@ int launch_alpha_beta_tcgen05(const float *match, const float *links, const int6
   TileLayout lay = TileLayout::make(L, M);
   dim3 grid(B, grad ? 2 : 1);
   const size_t smem = dp4_smem_bytes(M, L);
-  static const bool dbg = getenv("DAGB200_DP4_DEBUG") != nullptr;
+  static const int dbg = getenv("DAGB200_DP4_DEBUG") ? atoi(getenv("DAGB200_DP4_DEBUG")) : 0;
   cudaFuncSetAttribute(dag_alpha_beta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dag_alpha_beta_tcgen05_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
-                                                              M, L, Tl, lay, status, dbg ? 1 : 0);
+                                                              M, L, Tl, lay, status, dbg);
   DAGB200_CHECK_LAUNCH("dag_alpha_beta_tcgen05_kernel");
   prof_mark(2, st);
   return 0;
