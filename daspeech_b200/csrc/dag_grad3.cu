@@ -24,7 +24,7 @@ namespace dagb200 {
 namespace g3 {
 
 constexpr int kNegBig = -(1 << 20);
-constexpr int kBI = 128, kBN = 64, kKc = 16, kThreads = 256, kStages = 4;
+constexpr int kBI = 128, kBN = 64, kKc = 16, kThreads = 256, kStages = 3;
 constexpr int kPA = kBI + 8, kPB = kBN + 8;       // bf16 row pitch (odd multiple of 16 bytes: conflict-free ldmatrix)
 constexpr int kCP = kBN + 4;                      // float pitch of the staged output tile
 constexpr double kL2E_D = 1.4426950408889634074;
@@ -194,9 +194,12 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
 
   // shared memory: operand stages | per-warp scale tables [8][Mp] bf16 | per-pair epilogue exponents
   Stage *stg = reinterpret_cast<Stage *>(g3_smem);
-  int *fsum = reinterpret_cast<int *>(g3_smem + kStages * sizeof(Stage));                       // [8][Mp]
-  __nv_bfloat16 *stab = reinterpret_cast<__nv_bfloat16 *>(fsum + 8 * Mp);                       // [8][Mp]
-  float *dpair = reinterpret_cast<float *>(stab + 8 * Mp);                         // [8]
+  int *fsum = reinterpret_cast<int *>(g3_smem + (kStages - 1) * sizeof(Stage));                 // [8][Mp], aliases the last
+                                                                                                // stage (free in the prologue)
+  unsigned char *stab = g3_smem + kStages * sizeof(Stage);                                      // [8][Mp] biased exponents
+  float *lks = reinterpret_cast<float *>(stab + 8 * Mp);                                        // [128][64] links tile
+  float *dpair = lks + kBI * kBN;                                                               // [8]
+  if ((size_t)8 * Mp * sizeof(int) > sizeof(Stage)) fsum = reinterpret_cast<int *>(dpair + 8);  // long targets: own region
   float *cs = reinterpret_cast<float *>(g3_smem);                                  // [128][kCP] after the K loop
 
   const bool compute = nsteps > 0 && i0 < O && n0 < O;
@@ -217,14 +220,19 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
     const int *FA = reinterpret_cast<const int *>(ws + pl.off_fa) + (size_t)b * M * pl.NBp;
     const int *FB = reinterpret_cast<const int *>(ws + pl.off_fb) + (size_t)b * M * pl.NBp;
     const int nchunks = (nsteps + kKc - 1) / kKc;
-    // pull my links tile (read by the epilogue) towards L2: 128 rows x 256 bytes, 3 lines per row cover the segment
-    for (int x = tid; x < kBI * 3; x += kThreads) {
-      const int ii = x / 3, seg = x % 3;
-      const int i = i0 + ii;
-      const int k = max(0, n0 - i - 1) + seg * 32;
-      if (i < O && k < Tl && k < n0 + kBN - i - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(E + (int64_t)i * Tl + k));
+    // my links tile (read by the epilogue) starts travelling to shared memory now: 128 rows x 64 transitions, 4-byte
+    // cp.async granules (the rows are not 16-byte aligned), first commit group
+    for (int x = tid; x < kBI * kBN; x += kThreads) {
+      const int ii = x >> 6, nn = x & 63;
+      const int i = i0 + ii, n = n0 + nn, k = n - i - 1;
+      if (i < O && n < O && k >= 0 && k < Tl) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(lks + x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(E + (int64_t)i * Tl + k) : "memory");
+      } else {
+        lks[x] = neg_inf_f();
+      }
     }
-
+    asm volatile("cp.async.commit_group;" ::: "memory");
     // one chunk of 16 target rows: A rows t, B rows t + 1, 768 16-byte cp.async granules = 3 per thread with fixed
     // (row, plane, column) roles, so the addressing is done once
     const __nv_bfloat16 *gsrc[3];
@@ -271,7 +279,7 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
     {
       const int blkI = i0 / 32 + wi, blkN = n0 / 32 + wn;
       int *sums = fsum + warp * Mp;
-      __nv_bfloat16 *st = stab + warp * Mp;
+      unsigned char *st = stab + warp * Mp;
       int fmx = kNegBig;
       const int *pa = FA + blkI + (size_t)lane * pl.NBp, *pb = FB + blkN + (size_t)(lane + 1) * pl.NBp;
       const size_t step = (size_t)32 * pl.NBp;
@@ -285,16 +293,17 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
       fmx = __reduce_max_sync(0xffffffffu, fmx);
       const int mpad = (nsteps + kKc - 1) / kKc * kKc;
       for (int t = lane; t < mpad; t += 32) {
-        unsigned short bits = 0;
+        unsigned char bits = 0;                                // biased bf16 exponent of the scale (0: scale 0)
         if (t < nsteps) {
           const int d = sums[t] - fmx;                         // <= 0 (or hugely negative: no mass)
-          if (d >= -126) bits = (unsigned short)((d + 127) << 7);
+          if (d >= -126) bits = (unsigned char)(d + 127);
         }
-        st[t] = __ushort_as_bfloat16(bits);
+        st[t] = bits;
       }
       if (lane == 0) dpair[warp] = fmx > kNegBig ? (float)((double)fmx - (double)Z * kL2E_D) : 0.f;
       __syncwarp();
     }
+    __syncthreads();   // the frame sums alias the last operand stage, which the loop below starts filling
     // a pair entirely on or below the diagonal, beyond the graph or without any live row contributes nothing
     const bool pair_on = (n0 + 32 * wn + 31 > i0 + 32 * wi) && (i0 + 32 * wi < O) && (n0 + 32 * wn < O);
 
@@ -306,9 +315,9 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
       if (pair_on) {
         const Stage &S = stg[c % kStages];
         const int tig = lane & 3;
-        const __nv_bfloat16 *st = stab + warp * Mp + c * kKc;
-        const uint32_t s_lo = *reinterpret_cast<const uint32_t *>(st + 2 * tig);
-        const uint32_t s_hi = *reinterpret_cast<const uint32_t *>(st + 2 * tig + 8);
+        const unsigned char *st = stab + warp * Mp + c * kKc;
+        const uint32_t s_lo = ((uint32_t)st[2 * tig] << 7) | ((uint32_t)st[2 * tig + 1] << 23);
+        const uint32_t s_hi = ((uint32_t)st[2 * tig + 8] << 7) | ((uint32_t)st[2 * tig + 9] << 23);
         if (__any_sync(0xffffffffu, (s_lo | s_hi) != 0u)) {
           uint32_t bh[4][2], bl[4][2];
 #pragma unroll
@@ -359,16 +368,6 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
   // ---- epilogue: gl = go * exp2(links * log2e + Fmax - Z log2e) * G, one coalesced write per row, zeros elsewhere.
   // A warp owns 16 rows; their 32 transition values are fetched first (independent loads), then combined.
   const bool last_col = (n0 + kBN >= L);
-  float lk[16][2];
-#pragma unroll
-  for (int r = 0; r < 16; r++) {
-    const int ii = warp + 8 * r, i = i0 + ii;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int n = n0 + lane + 32 * h, k = n - i - 1;
-      lk[r][h] = (compute && i < O && n < O && k >= 0 && k < Tl) ? __ldg(E + (int64_t)i * Tl + k) : neg_inf_f();
-    }
-  }
 #pragma unroll
   for (int r = 0; r < 16; r++) {
     const int ii = warp + 8 * r, i = i0 + ii;
@@ -380,7 +379,7 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
       const int n = n0 + nn, k = n - i - 1;
       if (k < 0 || k >= Tl) continue;
       float v = 0.f;
-      if (compute && i < O && n < O) v = gout * exp2f(fmaf(lk[r][h], kL2E, dpair[(ii >> 5) * 2 + h])) * cs[ii * kCP + nn];
+      if (compute && i < O && n < O) v = gout * exp2f(fmaf(lks[ii * kBN + nn], kL2E, dpair[(ii >> 5) * 2 + h])) * cs[ii * kCP + nn];
       grow[k] = v;
     }
     if (last_col) {  // transitions that point beyond the padded graph: k >= L-1-i
@@ -392,7 +391,8 @@ grad_links_planes_kernel(const float *__restrict__ go, const float *__restrict__
 int padded_rows(int M) { return (M + 15) / 16 * 16; }
 size_t mma_smem_bytes(int M) {
   const int Mp = padded_rows(M);
-  const size_t a = kStages * sizeof(Stage) + (size_t)8 * Mp * 6 + 8 * sizeof(float) + 64;
+  size_t a = kStages * sizeof(Stage) + (size_t)8 * Mp + sizeof(float) * kBI * kBN + 8 * sizeof(float) + 64;
+  if ((size_t)8 * Mp * sizeof(int) > sizeof(Stage)) a += (size_t)8 * Mp * sizeof(int);
   const size_t c = sizeof(float) * kBI * kCP;
   return a > c ? a : c;
 }
