@@ -41,6 +41,12 @@ constexpr float kLn2Hi = 0.693359375f;          // 355/512: k * kLn2Hi is exact 
 constexpr float kLn2Lo = -2.12194440e-4f;       // ln2 - kLn2Hi
 
 __device__ long long g_dbg[8];
+__device__ long long g_dbg2[16];
+__device__ long long g_tl[6][32][4];
+__device__ long long g_ev[4][64][4];   // item event log of one block (debug)
+__device__ int g_evq = 27;
+__device__ long long g_ep[2][32][4];
+__device__ int g_evbase[4];
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -89,6 +95,15 @@ __device__ __forceinline__ int ld_acquire_s32(const int *p) {
   asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
   return v;
 }
+// 64-bit shared-memory mailbox word (value + tag in the sign bit): one relaxed scalar access each way, no fence
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const void *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.cta.shared.b64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(void *p, unsigned long long v) {
+  asm volatile("st.relaxed.cta.shared.b64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v));
+}
 __device__ __forceinline__ void st_release_s32(int *p, int v) {
   asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
@@ -130,6 +145,9 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// writer-side fences towards the async proxy by state space (the generic form above costs a GPU-scope MEMBAR)
+__device__ __forceinline__ void proxy_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // thread = row: 32 consecutive fp32 columns of my TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -156,7 +174,8 @@ struct Smem {
   float *io;        // [2][kCW][kTileF]    emission weights in (high words of fp64) -> incoming masses out (high words);
                     //                     written / drained by the epilogue warps one block ahead / behind the chain
   float *rmxs;      // [2][kCW][32]        per-column transition maximum folded into the emission weights (alpha: 0 where a vertex has no successor)
-  double *hand;     // [kCW][32]           predecessor sums of a chunk's last row, handed to the next chunk
+  double *hand;     // [2][kCW][32]        predecessor sums of a chunk's last row, handed to the next chunk: mailbox words
+                    //                     (the sums are >= 0; the sign bit carries the tag (step >> 1) & 1, slot = step & 1)
   int *fbuf;        // [kCW][32]           far frames of the rows of the current tile
   int *prog;        // [kCW]               progress counters of the chain warps (events)
   int *tanchor;     // [kCW]               fp64 frame of each chain warp's current tile
@@ -189,48 +208,63 @@ __device__ __forceinline__ int rm_load(const short *p) { const int v = *p; retur
 
 // high word of the fp64 emission weight exp(em + rmx) (21 significant bits; 0 when it vanishes)
 __device__ __forceinline__ int ew_word(float em, float rmx) {
+  // branch-free, so that the 16 independent weights of a pre-pass batch interleave
   const float w2 = (em + rmx) * kLog2e;
-  int word = 0;
-  if (w2 > -1.0e30f) {
-    const float wf = floorf(w2);
-    const int fb = __float_as_int(exp2f(w2 - wf));            // [1, 2]
-    const int iw = (int)wf + ((fb >> 23) - 127);
-    if (iw > -1023 && iw < 1024) word = ((iw + 1023) << 20) | ((fb & 0x7fffff) >> 3);
-  }
-  return word;
+  const float wc = fmaxf(w2, -2000.f);                        // -inf / NaN -> far below the fp64 range -> 0
+  const float wf = floorf(wc);
+  float fb;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(fb) : "f"(wc - wf));   // [1, 2]
+  const int fbi = __float_as_int(fb);
+  const int iw = (int)wf + ((fbi >> 23) - 127);
+  const int word = ((iw + 1023) << 20) | ((fbi & 0x7fffff) >> 3);
+  return (iw > -1023 && iw < 1024) ? word : 0;
 }
 
 // ---- epilogue-warp side jobs (lanes = columns): emission weights of a block BEFORE the chain warps reach it, lattice
 // values of a block AFTER they left it.  Both touch global memory, off the chain warps' critical path.
+// Split in two so that no global-memory latency sits at the head of a phase: `stage` starts asynchronous copies
+// (cp.async, 4 bytes each: any L) of the raw emissions into the tile and returns the column's transition maximum;
+// `convert` (same warp, after the phase's accumulator takes) turns them into weights in place.
 template <bool BETA>
-__device__ __forceinline__ void epi_prepass(const Geo &g, const Smem &sm, const float *__restrict__ match,
-                                            const float *__restrict__ g_rmax, int p, int qn, int ew, int lane) {
+__device__ __forceinline__ float epi_prepass_stage(const Geo &g, const Smem &sm, const float *__restrict__ match,
+                                                   const float *__restrict__ g_rmax, int p, int qn, int ew, int lane) {
   const int c = p * kCW + ew;
   const int Jn = BETA ? g.NBv - 1 - qn : qn;
   const int jn = kBlk * Jn + lane;
   float *iot = sm.io + ((size_t)(qn & 1) * kCW + ew) * kTileF;
-  float rmxn = jn < g.O ? __ldg(g_rmax + jn) : neg_inf_f();
+  const float rmxn = jn < g.O ? __ldg(g_rmax + jn) : neg_inf_f();
+  const int jc = min(jn, g.L - 1);
+#pragma unroll 8
+  for (int rr = 0; rr < 32; rr++) {
+    const int sr = c * 32 + rr;
+    const int tr = min(max(BETA ? g.Tn - 2 - sr : 1 + sr, 0), g.M - 1);
+    cp_async_f32(iot + rr * kPitch + lane, match + (int64_t)tr * g.L + jc);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  return rmxn;
+}
+template <bool BETA>
+__device__ __forceinline__ void epi_prepass_convert(const Geo &g, const Smem &sm, float rmxn, int p, int qn, int ew, int lane) {
+  const int c = p * kCW + ew;
+  const int Jn = BETA ? g.NBv - 1 - qn : qn;
+  const int jn = kBlk * Jn + lane;
+  float *iot = sm.io + ((size_t)(qn & 1) * kCW + ew) * kTileF;
   // alpha masses carry exp(rmax) of their own vertex; a vertex without successors (rmax = -inf) still has a forward
   // value and its mass meets only zero transitions, so its weight is taken without the factor
   if (!BETA && jn < g.O && rmxn == neg_inf_f()) rmxn = 0.f;
   sm.rmxs[((qn & 1) * kCW + ew) * 32 + lane] = rmxn;
-  const int jc = min(jn, g.L - 1);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 1
-  for (int h = 0; h < 2; h++) {          // two batches of 16 independent loads
+  for (int h = 0; h < 2; h++) {          // two batches of 16 independent weights
     float em[16];
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-      const int sr = c * 32 + 16 * h + r;
-      const int tr = min(max(BETA ? g.Tn - 2 - sr : 1 + sr, 0), g.M - 1);
-      em[r] = __ldg(match + (int64_t)tr * g.L + jc);
-    }
+    for (int r = 0; r < 16; r++) em[r] = iot[(16 * h + r) * kPitch + lane];
 #pragma unroll
     for (int r = 0; r < 16; r++) {
       const int rr = 16 * h + r, sr = c * 32 + rr;
       const int tr = BETA ? g.Tn - 2 - sr : 1 + sr;
-      int word = 0;
-      if (sr < g.nsteps && jn >= tr && jn < g.O) word = ew_word(em[r], rmxn);
-      iot[rr * kPitch + lane] = __int_as_float(word);
+      const int word = ew_word(em[r], rmxn);
+      iot[rr * kPitch + lane] = __int_as_float((sr < g.nsteps && jn >= tr && jn < g.O) ? word : 0);
     }
   }
 }
@@ -267,7 +301,8 @@ __device__ __forceinline__ void publish_row(const Geo &g, const Smem &sm, unsign
 template <bool BETA>
 __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const float *__restrict__ match,
                                              double *__restrict__ passd, int *__restrict__ passf,
-                                             unsigned char *__restrict__ aop, int p, int q, int cw, int lane, int ustep) {
+                                             unsigned char *__restrict__ aop, int p, int q, int cw, int lane, int ustep,
+                                             int &Fh_pre, double &hv_pre) {
   const int c = p * kCW + cw;
   const int J = BETA ? g.NBv - 1 - q : q;
   const int jbase = kBlk * J;
@@ -282,6 +317,7 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   const bool feeds_next = (c + 1 < g.NCv);       // somebody consumes my last row
   const bool to_pass = feeds_next && cw == kCW - 1;
 
+  const long long sgE = g.dbg ? clock64() : 0;
   // (2) frames: far frames of my rows, the frame handed from the chunk above, the fp64 frame of this tile
   const int FI = sm.fbuf[cw * 32 + lane];
   const int maxFI = __reduce_max_sync(0xffffffffu, FI);
@@ -289,9 +325,19 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   double hv = 0.0;                               // cw == 0: lane cj holds the handed sum of column cj
   int known = 0;                                 // cw > 0: last progress value seen of the warp above
   const int evbase = q * kEv;
+  unsigned long long *hand_w = reinterpret_cast<unsigned long long *>(sm.hand) + ((ustep & 1) * kCW + cw) * 32;
+  const unsigned long long *hand_r = hand_w - 32;
+  const unsigned long long tagbit = (unsigned long long)((ustep >> 1) & 1) << 63;
   if (cw == 0) {
-    Fh = passf[(p & 1) * g.NB + q];
-    hv = passd[((size_t)(p & 1) * g.NB + q) * 32 + lane];
+    // handed in from the previous pass (or the seed) through global memory; fetched one block ahead
+    Fh = Fh_pre;
+    hv = hv_pre;
+    int pn = p, qn = q + 1;
+    if (qn >= g.NBv) { pn = p + 1; qn = 0; }
+    if (pn < g.NP) {
+      Fh_pre = passf[(pn & 1) * g.NB + qn];
+      hv_pre = passd[((size_t)(pn & 1) * g.NB + qn) * 32 + lane];
+    }
   } else {
     do { known = ld_acquire_s32(sm.prog + cw - 1); } while (known < evbase + 1);
     Fh = sm.tanchor[cw - 1];
@@ -300,9 +346,9 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   const int Ft = dead ? kNegBig : max(maxFI, Fh - 600);
   if (feeds_next && !to_pass) {
     if (lane == 0) sm.tanchor[cw] = Ft;
-    if (dead) sm.hand[cw * 32 + lane] = 0.0;
+    if (dead) st_relaxed_u64(hand_w + lane, tagbit);          // tagged zeros
     __syncwarp();
-    if (lane == 0) st_release_s32(sm.prog + cw, dead ? evbase + kEv : evbase + 1);
+    if (lane == 0) st_release_s32(sm.prog + cw, evbase + 1);
   }
   if (to_pass) {
     if (lane == 0) passf[((p + 1) & 1) * g.NB + q] = Ft;
@@ -314,26 +360,32 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
     for (int k = 0; k < 32; k++) { iow[k] = neg_inf_f(); mrow[k] = 0.f; }
     rm_store(sm.rmtab + (cw * 32 + lane + 1) * g.NB + q, kNegBig);
     publish_row(g, sm, aop, mrow, p, q, cw, lane, true);
-    proxy_fence_async();
+    proxy_fence_async_smem();
+    proxy_fence_async_global();
     __syncwarp();
     return;
   }
   // (3) the fp64 push table of this block
+  const bool swdbg = g.dbg && blockIdx.x == 0 && lane == 0 && (cw == 0 || cw == 7);
+  const long long sg0 = swdbg ? clock64() : 0;
   mbar_wait(sm.ubar, ustep & 1);
+  long long sgA = 0, sgB = 0;
+  const long long sg1 = swdbg ? clock64() : 0;
   const double *ut = sm.ut;
   const double hs = pow2d(Fh - Ft);              // handed sums are in the frame of the tile above
   const double xs = pow2d(FI - Ft);              // far sums of my row are in the frame FI
   int maxhi = 0;
 
   // (4) column sweep: four groups of 8 columns (runtime loop keeps the code small)
-  const bool swdbg = g.dbg && blockIdx.x == 0 && lane == 0 && (cw == 0 || cw == 7);
   const long long sw0 = swdbg ? clock64() : 0;
 #pragma unroll 1
   for (int G = 0; G < 4; G++) {
+    const long long sa0 = swdbg ? clock64() : 0;
     double a[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = 0.0;
     // predecessor sums from the completed groups of my own row (masses re-read with 21 significant bits)
+#pragma unroll 4
     for (int ci = 0; ci < 8 * G; ci++) {
       const int w = __float_as_int(mrow[BETA ? 31 - ci : ci]);
       const double md = __hiloint2double(w, 0);
@@ -342,26 +394,25 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
       a[0] = fma(md, u0.x, a[0]); a[1] = fma(md, u0.y, a[1]); a[2] = fma(md, u1.x, a[2]); a[3] = fma(md, u1.y, a[3]);
       a[4] = fma(md, u2.x, a[4]); a[5] = fma(md, u2.y, a[5]); a[6] = fma(md, u3.x, a[6]); a[7] = fma(md, u3.y, a[7]);
     }
+    if (swdbg) sgA += clock64() - sa0;
+    unsigned long long zraw = (cw > 0) ? ld_relaxed_u64(hand_r + 8 * G) : 0ull;
 #pragma unroll
     for (int K = 0; K < 8; K++) {
       const int cj = 8 * G + K;
       const int jj = BETA ? 31 - cj : cj;
+      // hand my own last row to the chunk below
+      if (feeds_next && lane == 31) {
+        if (to_pass) passd[((size_t)((p + 1) & 1) * g.NB + q) * 32 + cj] = a[K];
+        else st_relaxed_u64(hand_w + cj, (unsigned long long)__double_as_longlong(a[K]) | tagbit);
+      }
       // what the row above hands to this column (lane 0: from the chunk above / the previous pass)
       double z;
       if (cw == 0) {
         z = __shfl_sync(0xffffffffu, hv, cj) * hs;
       } else {
-        while (known < evbase + 2 + cj) known = ld_acquire_s32(sm.prog + cw - 1);
-        z = sm.hand[(cw - 1) * 32 + cj] * hs;
-      }
-      // hand my own last row to the chunk below
-      if (feeds_next && lane == 31) {
-        if (to_pass) {
-          passd[((size_t)((p + 1) & 1) * g.NB + q) * 32 + cj] = a[K];
-        } else {
-          sm.hand[cw * 32 + cj] = a[K];
-          st_release_s32(sm.prog + cw, evbase + 2 + cj);
-        }
+        while ((zraw ^ tagbit) >> 63) zraw = ld_relaxed_u64(hand_r + cj);
+        z = __longlong_as_double((long long)(zraw & 0x7fffffffffffffffull)) * hs;
+        if (K < 7) zraw = ld_relaxed_u64(hand_r + cj + 1);     // usually already there: the chunk above runs ahead
       }
       double rm = __shfl_up_sync(0xffffffffu, a[K], 1);
       if (lane == 0) rm = z;
@@ -378,32 +429,51 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
       }
     }
   }
-  if (swdbg) atomicAdd((unsigned long long *)&g_dbg[4 + (cw == 7 ? 1 : 0) + (BETA ? 2 : 0)], (unsigned long long)(clock64() - sw0));
+  const long long sg2 = swdbg ? clock64() : 0;
   // (5) row frame and normalised masses (value / 2^maxe < 1) for the A-operand fragments
   const int emf = maxhi >> 20;                   // biased exponent of the largest mass of my row (0: none)
   const int maxe = (emf > 0) ? Ft + emf - 1022 : kNegBig;
   rm_store(sm.rmtab + (cw * 32 + lane + 1) * g.NB + q, maxe);
   const float *rmxw = sm.rmxs + ((q & 1) * kCW + cw) * 32;
-#pragma unroll 8
-  for (int k = 0; k < 32; k++) {
-    const int w = __float_as_int(mrow[k]);
-    const int we = w >> 20;
-    // lattice value = log(outgoing mass) - rmax (alpha) / log(outgoing mass) (beta), off the dependency path
-    float out = neg_inf_f();
-    if (we > 0) {
+#pragma unroll 1
+  for (int k0 = 0; k0 < 32; k0 += 8) {           // batches of 8: all loads, the arithmetic, all stores
+    int w[8];
+    float rx[8], out[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { w[k] = __float_as_int(mrow[k0 + k]); rx[k] = BETA ? 0.f : rmxw[k0 + k]; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int we = w[k] >> 20;
+      // lattice value = log(outgoing mass) - rmax (alpha) / log(outgoing mass) (beta), off the dependency path; branch-free
       const float fl = (float)(we - 1023 + Ft);
-      out = fmaf(__log2f(__int_as_float(0x3f800000 | ((w & 0xfffff) << 3))), 0.6931471805599453f, fl * kLn2Lo) + fl * kLn2Hi;
-      if (!BETA) out -= rmxw[k];
+      float lg;
+      asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(__int_as_float(0x3f800000 | ((w[k] & 0xfffff) << 3))));   // mantissa in [1, 2)
+      float o = fmaf(lg, 0.6931471805599453f, fl * kLn2Lo) + fl * kLn2Hi;
+      if (!BETA) o -= rx[k];
+      out[k] = (we > 0) ? o : neg_inf_f();
+      const int fe = we - emf + 126;
+      w[k] = (we > 0 && fe > 0) ? ((fe << 23) | ((w[k] & 0xfffff) << 3)) : 0;
     }
-    iow[k] = out;
-    const int fe = we - emf + 126;
-    const int bits = (we > 0 && fe > 0) ? ((fe << 23) | ((w & 0xfffff) << 3)) : 0;
-    mrow[k] = __int_as_float(bits);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { iow[k0 + k] = out[k]; mrow[k0 + k] = __int_as_float(w[k]); }
   }
   // (6) the row as A operand of the tensor cores (shared memory for the next block, global memory for the later ones)
+  const long long sg3 = swdbg ? clock64() : 0;
   publish_row(g, sm, aop, mrow, p, q, cw, lane, false);
-  proxy_fence_async();
+  const long long sg4 = swdbg ? clock64() : 0;
+  proxy_fence_async_smem();
+  proxy_fence_async_global();
   __syncwarp();
+  if (swdbg) {
+    const int o = (cw == 7 ? 8 : 0);
+    atomicAdd((unsigned long long *)&g_dbg2[o + 0], (unsigned long long)(sg1 - sg0));      // wait push table
+    atomicAdd((unsigned long long *)&g_dbg2[o + 1], (unsigned long long)sgA);              // re-entry loops
+    atomicAdd((unsigned long long *)&g_dbg2[o + 2], (unsigned long long)(sg2 - sw0 - sgA));// column steps
+    atomicAdd((unsigned long long *)&g_dbg2[o + 3], (unsigned long long)(sg3 - sg2));      // normalisation
+    atomicAdd((unsigned long long *)&g_dbg2[o + 4], (unsigned long long)(sg4 - sg3));      // publish
+    atomicAdd((unsigned long long *)&g_dbg2[o + 5], (unsigned long long)(clock64() - sg4));// fence
+    atomicAdd((unsigned long long *)&g_dbg2[o + 6], (unsigned long long)(sg0 - sgE));      // entry .. push-table wait
+  }
 }
 
 // phase 2 of a chain warp: the lattice rows of the block (lanes = columns, coalesced)
@@ -479,9 +549,17 @@ __device__ __forceinline__ void producer_run(Producer &pr, const Geo &g, const S
 // MMA issuer (one thread): the 6 MMAs of item n (A: ring stage or sm.afresh), then the two commits
 struct Issuer {
   int n;             // items whose MMAs have been issued
-  bool dbg;
+  bool dbg, logq;
+  int logbase;
   long long t_full, t_tempty, t_p1, t_p2;
 };
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+// The whole issuer warp runs this with warp-uniform values (the descriptors then live in uniform registers and the
+// UTCHMMA issue needs no per-instruction vector->uniform transfer); one elected lane issues.
 __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t tmem_base, uint32_t ring_u32, uint32_t afresh_u32,
                                            bool from_afresh, int mt) {
   const int st = is.n % kStages, pp = is.n % kTSlots, k = is.n / kTSlots;
@@ -489,7 +567,8 @@ __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t 
   mbar_wait(sm.full + st, (is.n / kStages) & 1);
   long long c1 = is.dbg ? clock64() : 0;
   if (k >= 1) mbar_wait(sm.tempty + pp, (k - 1) & 1);
-  if (is.dbg) { is.t_full += c1 - c0; is.t_tempty += clock64() - c1; }
+  long long c2 = is.dbg ? clock64() : 0;
+  if (is.dbg) { is.t_full += c1 - c0; is.t_tempty += c2 - c1; }
   tc_fence_after();
   const uint32_t stage = ring_u32 + st * kStageBytes;
   const uint32_t d = tmem_base + pp * 32;
@@ -499,18 +578,25 @@ __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t 
   const uint32_t a0 = (from_afresh ? afresh_u32 + mt * 2048 : stage) >> 4;
   const uint32_t aplane = (from_afresh ? 16384u : 8192u) >> 4, akstep = (from_afresh ? 8192u : 4096u) >> 4;
   const uint32_t b0 = (stage + 16384) >> 4;
+  if (elect_one()) {
 #pragma unroll
-  for (int ks = 0; ks < 2; ks++) {
-    const uint64_t ahi = dA | (uint64_t)((a0 + ks * akstep) & 0x3fff);
-    const uint64_t alo = dA | (uint64_t)((a0 + aplane + ks * akstep) & 0x3fff);
-    const uint64_t bhi = dB | (uint64_t)((b0 + ks * 64) & 0x3fff);
-    const uint64_t blo = dB | (uint64_t)((b0 + 128 + ks * 64) & 0x3fff);
-    umma_f16(d, ahi, bhi, ks > 0 ? 1u : 0u);
-    umma_f16(d, alo, bhi, 1u);
-    umma_f16(d, ahi, blo, 1u);
+    for (int ks = 0; ks < 2; ks++) {
+      const uint64_t ahi = dA | (uint64_t)((a0 + ks * akstep) & 0x3fff);
+      const uint64_t alo = dA | (uint64_t)((a0 + aplane + ks * akstep) & 0x3fff);
+      const uint64_t bhi = dB | (uint64_t)((b0 + ks * 64) & 0x3fff);
+      const uint64_t blo = dB | (uint64_t)((b0 + 128 + ks * 64) & 0x3fff);
+      umma_f16(d, ahi, bhi, ks > 0 ? 1u : 0u);
+      umma_f16(d, alo, bhi, 1u);
+      umma_f16(d, ahi, blo, 1u);
+    }
+    umma_commit(sm.empty + st);     // the stage may be refilled once these MMAs have read it
+    umma_commit(sm.tfull + pp);     // ... and the accumulator slot is complete
   }
-  umma_commit(sm.empty + st);     // the stage may be refilled once these MMAs have read it
-  umma_commit(sm.tfull + pp);     // ... and the accumulator slot is complete
+  __syncwarp();
+  if (is.dbg && is.logq) {
+    const int i = is.n - is.logbase;
+    if (i >= 0 && i < 64) { g_ev[0][i][0] = c0; g_ev[0][i][1] = c1; g_ev[0][i][2] = c2; g_ev[0][i][3] = clock64(); }
+  }
   is.n++;
 }
 
@@ -519,30 +605,37 @@ struct Epi {
   float acc[32];
   int F;
   int n;            // items seen so far (all tiles), mirrors Issuer::n
+  int logbase;
 };
 
 // take one item: wait for its accumulator, read my row, release the slot, add with the power-of-two scale
-__device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_base, int quarter, int Fs, bool mine) {
+__device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_base, int quarter, int Fs, bool mine, int logrow = -1) {
   const int pp = e.n % kTSlots, k = e.n / kTSlots;
+  const int li = e.n - e.logbase;
   e.n++;
   if (!mine) return;
+  const bool lg = logrow >= 0 && li >= 0 && li < 64;
+  if (lg) g_ev[logrow][li][0] = clock64();
   mbar_wait(sm.tfull + pp, k & 1);
+  if (lg) g_ev[logrow][li][1] = clock64();
   tc_fence_after();
   float v[32];
   tmem_ld32(tmem_base + pp * 32 + ((uint32_t)(quarter * 32) << 16), v);
   tc_fence_before();
   __syncwarp();
   if ((threadIdx.x & 31) == 0) mbar_arrive(sm.tempty + pp);
+  if (lg) g_ev[logrow][li][2] = clock64();
   if (Fs > kNegBig) {
-    if (Fs > e.F) {
-      const float rs = pow2i(e.F - Fs);           // 0 when nothing has been accumulated yet
+    if (Fs > e.F) {   // the new source block sets the frame: acc = acc * 2^(F - Fs) + v  (the scale is 0 when acc is empty)
+      const float rs = pow2i(e.F - Fs);
 #pragma unroll
-      for (int j = 0; j < 32; j++) e.acc[j] *= rs;
+      for (int j = 0; j < 32; j++) e.acc[j] = fmaf(e.acc[j], rs, v[j]);
       e.F = Fs;
-    }
-    const float sc = pow2i(Fs - e.F);
+    } else {
+      const float sc = pow2i(Fs - e.F);
 #pragma unroll
-    for (int j = 0; j < 32; j++) e.acc[j] = fmaf(v[j], sc, e.acc[j]);
+      for (int j = 0; j < 32; j++) e.acc[j] = fmaf(v[j], sc, e.acc[j]);
+    }
   }
 }
 
@@ -551,7 +644,7 @@ __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_b
 template <bool BETA>
 __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict__ lat, unsigned char *__restrict__ ws,
                              const TileLayout &lay, const Smem &sm, int O, int Tn, int M, int L, int Tl, int dbgi) {
-  const bool dbg = dbgi != 0;
+  const bool dbg = (dbgi & 0xff) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float ninf = neg_inf_f();
   Geo g;
@@ -577,6 +670,8 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
     *reinterpret_cast<uint4 *>(aop + (size_t)(x >> 3) * (g.Mr >> 7) * 16384 + (size_t)(x & 7) * 2048) = make_uint4(0u, 0u, 0u, 0u);
   for (int x = threadIdx.x; x < g.NB * 32; x += kThreads) passd[x] = 0.0;                             // parity 0
   for (int x = threadIdx.x; x < g.NB; x += kThreads) passf[x] = kNegBig;
+  for (int x = threadIdx.x; x < 2 * kCW * 32; x += kThreads)          // mailboxes: tag 1 = nothing posted for steps 0, 1
+    reinterpret_cast<unsigned long long *>(sm.hand)[x] = 1ull << 63;
   if (threadIdx.x < kStages) { mbar_init(sm.full + threadIdx.x, 1); mbar_init(sm.empty + threadIdx.x, 1); }
   if (threadIdx.x < kTSlots) { mbar_init(sm.tfull + threadIdx.x, 1); mbar_init(sm.tempty + threadIdx.x, 4); }
   if (threadIdx.x == 0) mbar_init(sm.ubar, 1);
@@ -636,6 +731,20 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   long long t_p1 = 0, t_p2 = 0;
   // The roles run separate copies of the (pass, block) loops; they meet at the CTA barrier.
   auto cta_sync = [] { asm volatile("bar.sync 0;" ::: "memory"); };
+  long long t_b1 = 0, t_b2 = 0;
+  // debug timeline: arrival / release clocks of six observer threads at both barriers of every block (CTA 0, alpha)
+  const int tl_role = (!dbg || BETA || blockIdx.x != 0 || lane != 0) ? -1
+                      : (warp == 0 ? 0 : warp == 7 ? 1 : warp == 8 ? 2 : warp == 15 ? 3 : warp == kIssuerWarp ? 4 : warp == kProducerWarp ? 5 : -1);
+  auto cta_sync1 = [&](int q) {
+    if (tl_role >= 0 && q < 32) g_tl[tl_role][q][0] = clock64();
+    asm volatile("bar.sync 0;" ::: "memory");
+    if (tl_role >= 0 && q < 32) g_tl[tl_role][q][1] = clock64();
+  };
+  auto cta_sync2 = [&](int q) {
+    if (tl_role >= 0 && q < 32) g_tl[tl_role][q][2] = clock64();
+    asm volatile("bar.sync 0;" ::: "memory");
+    if (tl_role >= 0 && q < 32) g_tl[tl_role][q][3] = clock64();
+  };
 
   if (warp == kProducerWarp) {
     // ================================ TMA producer (one thread) ========================================
@@ -659,7 +768,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
           producer_run<BETA>(pr, g, sm, aop, tiles, lay, p, q - 1, consumed + kStages);
         }
         __syncwarp();
-        cta_sync();
+        cta_sync1(q);
         if (lane == 0) {
           if (have || p + 1 < g.NP) {   // push table of the next block (the chain warps are done with this one)
             const int qn = have ? q + 1 : 0;
@@ -671,48 +780,56 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
           producer_run<BETA>(pr, g, sm, aop, tiles, lay, p, q, consumed + kStages);
         }
         __syncwarp();
-        cta_sync();
+        cta_sync2(q);
       }
     }
   } else if (warp == kIssuerWarp) {
-    // ================================ MMA issuer (one thread) ==========================================
+    // ================================ MMA issuer (one warp, one elected lane issues) =====================
     Issuer is;
     is.n = 0;
     is.dbg = dbg && blockIdx.x == 0 && lane == 0;
     is.t_full = is.t_tempty = is.t_p1 = is.t_p2 = 0;
-    const uint32_t ring_u32 = smem_u32(sm.ring), afresh_u32 = smem_u32(sm.afresh);
-    for (int p = 0; p < g.NP; p++) {
-      const int ntl = (g.NCv - kCW * p > 4) ? 2 : 1;
+    is.logq = false; is.logbase = 0;
+    // everything that shapes the item sequence as warp-uniform values
+    const uint32_t ring_u32 = __shfl_sync(0xffffffffu, smem_u32(sm.ring), 0);
+    const uint32_t afresh_u32 = __shfl_sync(0xffffffffu, smem_u32(sm.afresh), 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int uNP = __shfl_sync(0xffffffffu, g.NP, 0), uNBv = __shfl_sync(0xffffffffu, g.NBv, 0);
+    const int uNCv = __shfl_sync(0xffffffffu, g.NCv, 0), uband = __shfl_sync(0xffffffffu, g.band, 0);
+    for (int p = 0; p < uNP; p++) {
+      const int ntl = (uNCv - kCW * p > 4) ? 2 : 1;
       cta_sync();
-      for (int q = 0; q < g.NBv; q++) {
+      for (int q = 0; q < uNBv; q++) {
         const int J = q + 1;
-        const bool have = J < g.NBv;
+        const bool have = J < uNBv;
         long long i0 = is.dbg ? clock64() : 0;
-        if (lane == 0 && have) {
-          for (int qs = max(0, J - g.band); qs <= J - 2; qs++)
-            for (int mt = 0; mt < ntl; mt++) issuer_mma(is, sm, tmem_base, ring_u32, afresh_u32, false, mt);
+        is.logq = is.dbg && !BETA && q == g_evq;
+        if (is.logq) { is.logbase = is.n; g_evbase[0] = is.n; g_ev[3][0][0] = i0; }
+        if (have) {
+          for (int qs = max(0, J - uband); qs <= J - 2; qs++)
+            for (int mt = 0; mt < ntl; mt++) issuer_mma(is, sm, tmem_u, ring_u32, afresh_u32, false, mt);
         }
-        __syncwarp();
         long long i1 = is.dbg ? clock64() : 0;
-        cta_sync();
+        cta_sync1(q);
         long long i2 = is.dbg ? clock64() : 0;
-        if (lane == 0 && have) {
+        is.logq = false;
+        if (have) {
           tc_fence_after();
-          for (int mt = 0; mt < ntl; mt++) issuer_mma(is, sm, tmem_base, ring_u32, afresh_u32, true, mt);
+          for (int mt = 0; mt < ntl; mt++) issuer_mma(is, sm, tmem_u, ring_u32, afresh_u32, true, mt);
         }
-        __syncwarp();
         if (is.dbg) { is.t_p1 += i1 - i0; is.t_p2 += clock64() - i2; }
-        cta_sync();
+        cta_sync2(q);
       }
     }
-    if (is.dbg) printf("[dp4 issuer %s] items %d  phase1 %lld  phase2 %lld  wait-full %lld  wait-tmem-empty %lld\n",
-                       BETA ? "beta" : "alpha", is.n, is.t_p1, is.t_p2, is.t_full, is.t_tempty);
+    if (is.dbg) printf("[dp4 issuer %s] items %d  phase1 %lld  phase2 %lld  wait-full %lld  wait-tmem-empty %lld  bar1 %lld bar2 %lld\n",
+                       BETA ? "beta" : "alpha", is.n, is.t_p1, is.t_p2, is.t_full, is.t_tempty, t_b1, t_b2);
   } else if (warp >= kCW) {
     // ================================ epilogue warps: thread = row ======================================
     const int ew = warp - kCW;                    // rows 32 ew .. 32 ew + 31 of the pass
     const int mymt = ew >> 2, quarter = ew & 3;   // TMEM lanes 32 quarter .. (this warp's lane window: warp % 4)
     Epi e;
     e.n = 0;
+    e.logbase = 0;
     const bool edbg = dbg && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 7);
     long long t_post = 0, t_pre = 0, t_take = 0;
     const int et = threadIdx.x - kCW * 32;
@@ -730,7 +847,10 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
         for (int x = lane; x < kTileF; x += 32) xo[x] = 0.f;
         sm.fbuf[ew * 32 + lane] = kNegBig;
       }
-      if (active) epi_prepass<BETA>(g, sm, match, g_rmax, p, 0, ew, lane);   // emission weights of block 0
+      if (active) {                                                          // emission weights of block 0
+        const float r0 = epi_prepass_stage<BETA>(g, sm, match, g_rmax, p, 0, ew, lane);
+        epi_prepass_convert<BETA>(g, sm, r0, p, 0, ew, lane);
+      }
       cta_sync();
       for (int q = 0; q < g.NBv; q++) {
         const int J = q + 1;
@@ -742,12 +862,13 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
           if (sr < g.nsteps && kBlk * J2 < g.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(match + (int64_t)tr * g.L + kBlk * J2));
         }
         long long e0 = edbg ? clock64() : 0;
-        if (active) {   // lattice values of the block the chain warps just left, emission weights of the next one
-          long long e1 = edbg ? clock64() : 0;
-          if (have) epi_prepass<BETA>(g, sm, match, g_rmax, p, q + 1, ew, lane);
-          if (edbg) { t_post += e1 - e0; t_pre += clock64() - e1; }
-        }
+        const int epr = (edbg && !BETA && q < 32) ? (ew == 0 ? 0 : 1) : -1;
+        if (epr >= 0) g_ep[epr][q][0] = e0;
+        float rmx_next = 0.f;
+        if (active && have) rmx_next = epi_prepass_stage<BETA>(g, sm, match, g_rmax, p, q + 1, ew, lane);   // raw emissions of the next block
+        if (edbg) t_post += clock64() - e0;
         long long e2 = edbg ? clock64() : 0;
+        if (epr >= 0) g_ep[epr][q][1] = e2;
         const bool tile_on = active && have && !tile_geo_dead<BETA>(g, c, BETA ? g.NBv - 1 - J : J);
         if (have) {
           // consumer row 0 of the pass (the last row of the previous pass / the seed) of block q for phase 2
@@ -755,20 +876,30 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
             const int pl = lane >> 2, kc = lane & 3;
             const uint4 v = *reinterpret_cast<const uint4 *>(aop + ((size_t)q * (g.Mr >> 7) + 2 * p) * 16384 + (size_t)(pl * 4 + kc) * 2048);
             *reinterpret_cast<uint4 *>(sm.afresh + ((size_t)(pl * 4 + kc) * 256) * 16) = v;
-            proxy_fence_async();
+            proxy_fence_async_smem();
           }
 #pragma unroll
           for (int j = 0; j < 32; j++) e.acc[j] = 0.f;
           e.F = kNegBig;
+          if (epr >= 0) g_ep[epr][q][2] = clock64();
           for (int qs = max(0, J - g.band); qs <= J - 2; qs++)
             for (int mt = 0; mt < ntl; mt++) {
               const bool mine = (mt == mymt);
               const int Fs = (mine && tile_on && rowvalid) ? rm_load(sm.rmtab + (ew * 32 + lane) * g.NB + qs) : kNegBig;
-              epi_take(e, sm, tmem_base, quarter, Fs, mine);
+              const int logrow = (dbg && !BETA && blockIdx.x == 0 && lane == 0 && q == g_evq && (ew == 0 || ew == 4)) ? (ew == 0 ? 1 : 2) : -1;
+              if (logrow >= 0 && qs == max(0, J - g.band) && mt == 0) e.logbase = e.n;
+              epi_take(e, sm, tmem_base, quarter, Fs, mine, logrow);
+              if (logrow >= 0) g_ev[logrow][e.n - 1 - e.logbase < 64 ? e.n - 1 - e.logbase : 63][3] = clock64();
             }
         }
         if (edbg) t_take += clock64() - e2;
-        cta_sync();
+        if (epr >= 0) g_ep[epr][q][3] = clock64();
+        {
+          const long long e3 = edbg ? clock64() : 0;
+          if (active && have) epi_prepass_convert<BETA>(g, sm, rmx_next, p, q + 1, ew, lane);                // ... into weights
+          if (edbg) t_pre += clock64() - e3;
+        }
+        cta_sync1(q);
         if (have) {
           for (int mt = 0; mt < ntl; mt++) {
             const bool mine = (mt == mymt);
@@ -782,12 +913,15 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
             sm.fbuf[ew * 32 + lane] = e.F;
           }
         }
-        cta_sync();
+        cta_sync2(q);
       }
     }
-    if (edbg) printf("[dp4 epilogue warp %d %s] post %lld  pre %lld  takes(phase 1) %lld\n", ew, BETA ? "beta" : "alpha", t_post, t_pre, t_take);
+    if (edbg) printf("[dp4 epilogue warp %d %s] post %lld  pre %lld  takes(phase 1) %lld  bar1 %lld bar2 %lld\n", ew, BETA ? "beta" : "alpha", t_post, t_pre, t_take, t_b1, t_b2);
   } else {
     // ================================ chain warps ================================
+    int Fh_pre = kNegBig;
+    double hv_pre = 0.0;
+    if (cw == 0) { Fh_pre = passf[0]; hv_pre = passd[lane]; }      // (pass 0, block 0): written by the prologue
     for (int p = 0; p < g.NP; p++) {
       const int c = p * kCW + cw;
       const bool active = c < g.NCv;
@@ -795,19 +929,47 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
       for (int q = 0; q < g.NBv; q++) {
         const int ustep = p * g.NBv + q;
         long long t0 = dbg ? clock64() : 0;
-        if (active) chain_phase1<BETA>(g, sm, match, passd, passf, aop, p, q, cw, lane, ustep);
+        if (active) chain_phase1<BETA>(g, sm, match, passd, passf, aop, p, q, cw, lane, ustep, Fh_pre, hv_pre);
         long long t1 = dbg ? clock64() : 0;
-        cta_sync();
+        cta_sync1(q);
         if (active) chain_phase2<BETA>(g, sm, lat, p, q, cw, lane);
         if (dbg) t_p1 += t1 - t0;
-        cta_sync();
+        cta_sync2(q);
       }
     }
   }
-  if (dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 7 * 32))
-    printf("[dp4 chain warp %d %s] phase1 %lld  phase2 %lld\n", warp, BETA ? "beta" : "alpha", t_p1, t_p2);
+  if (dbg && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 7 * 32)) {
+    const int o = (warp == 7 ? 8 : 0);
+    printf("[dp4 chain warp %d %s] bar1 %lld bar2 %lld\n", warp, BETA ? "beta" : "alpha", t_b1, t_b2);
+    printf("[dp4 chain warp %d %s] phase1 %lld  phase2 %lld | entry %lld wait-ut %lld reentry %lld columns %lld norm %lld publish %lld fence %lld (alpha+beta)\n",
+           warp, BETA ? "beta" : "alpha", t_p1, t_p2, g_dbg2[o + 6], g_dbg2[o + 0], g_dbg2[o + 1], g_dbg2[o + 2], g_dbg2[o + 3], g_dbg2[o + 4], g_dbg2[o + 5]);
+  }
   tc_fence_before();
   __syncthreads();
+  if (dbg && !BETA && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long z0 = g_ev[3][0][0];
+    printf("[dp4 items of block %d] issuer: start, full ok, tmem-empty ok, issued | epilogue (owner warp): start wait, tfull ok, ld done+released, fma done\n", g_evq);
+    for (int i = 0; i < 56; i++) {
+      const int r = (i & 1) ? 2 : 1;
+      printf("  item %2d  %6lld %6lld %6lld %6lld | %6lld %6lld %6lld %6lld\n", i, g_ev[0][i][0] - z0, g_ev[0][i][1] - z0, g_ev[0][i][2] - z0, g_ev[0][i][3] - z0,
+             g_ev[r][i][0] - z0, g_ev[r][i][1] - z0, g_ev[r][i][2] - z0, g_ev[r][i][3] - z0);
+    }
+    printf("[dp4 epilogue warps 0 / 7 per block] prepass start, prepass end, takes start, takes end (relative to chain 0 leaving barrier 2 of the previous block)\n");
+    for (int q = 1; q < min(g.NBv, 32); q++) {
+      const long long st = g_tl[4][q - 1][3];
+      printf("  q %2d  %6lld %6lld %6lld %6lld | %6lld %6lld %6lld %6lld\n", q, g_ep[0][q][0] - st, g_ep[0][q][1] - st, g_ep[0][q][2] - st, g_ep[0][q][3] - st,
+             g_ep[1][q][0] - st, g_ep[1][q][1] - st, g_ep[1][q][2] - st, g_ep[1][q][3] - st);
+    }
+    printf("[dp4 timeline alpha] per block: phase-1 length, then arrival at barrier 1 relative to its release (chain0 chain7 epi0 epi7 issuer producer), phase-2 length, same for barrier 2\n");
+    for (int q = 0; q < min(g.NBv, 32); q++) {
+      const long long rel1 = g_tl[0][q][1], rel2 = g_tl[0][q][3];
+      const long long start1 = q > 0 ? g_tl[0][q - 1][3] : rel1;
+      printf("  q %2d  p1 %6lld | %6lld %6lld %6lld %6lld %6lld %6lld | p2 %6lld | %6lld %6lld %6lld %6lld %6lld %6lld\n", q, rel1 - start1,
+             g_tl[0][q][0] - rel1, g_tl[1][q][0] - rel1, g_tl[2][q][0] - rel1, g_tl[3][q][0] - rel1, g_tl[4][q][0] - rel1, g_tl[5][q][0] - rel1,
+             rel2 - rel1,
+             g_tl[0][q][2] - rel2, g_tl[1][q][2] - rel2, g_tl[2][q][2] - rel2, g_tl[3][q][2] - rel2, g_tl[4][q][2] - rel2, g_tl[5][q][2] - rel2);
+    }
+  }
   if (warp == kIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -836,7 +998,7 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
   sm.ring = p;                               p += (size_t)kStages * kStageBytes;
   sm.afresh = p;                             p += 32768;
   sm.ut = reinterpret_cast<double *>(p);     p += 8192;
-  sm.hand = reinterpret_cast<double *>(p);   p += kCW * 32 * sizeof(double);
+  sm.hand = reinterpret_cast<double *>(p);   p += 2 * kCW * 32 * sizeof(double);
   sm.full = reinterpret_cast<uint64_t *>(p);   p += kStages * 8;
   sm.empty = reinterpret_cast<uint64_t *>(p);  p += kStages * 8;
   sm.tfull = reinterpret_cast<uint64_t *>(p);  p += kTSlots * 8;
@@ -861,7 +1023,7 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
 size_t dp4_smem_bytes(int M, int L) {
   using namespace dp4;
   TileLayout lay = TileLayout::make(L, M);
-  return (size_t)kStages * kStageBytes + 32768 + 8192 + kCW * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 +
+  return (size_t)kStages * kStageBytes + 32768 + 8192 + 2 * kCW * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 +
          (size_t)3 * kCW * kTileF * 4 + 2 * kCW * 32 * 4 + kCW * 32 * 4 + 2 * kCW * 4 + (size_t)257 * lay.NB * 2 + 64;
 }
 
