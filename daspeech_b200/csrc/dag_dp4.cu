@@ -174,7 +174,8 @@ struct Smem {
   float *io;        // [2][kCW][kTileF]    emission weights in (high words of fp64) -> incoming masses out (high words);
                     //                     written / drained by the epilogue warps one block ahead / behind the chain
   float *rmxs;      // [2][kCW][32]        per-column transition maximum folded into the emission weights (alpha: 0 where a vertex has no successor)
-  double *hand;     // [2][kCW][32]        predecessor sums of a chunk's last row, handed to the next chunk: mailbox words
+  double *hand;     // [2][kCW + 1][32]    row c = what chunk c receives (predecessor sums of the last row of the chunk above; row 0: of
+                    //                     the previous pass, posted by chunk 0 itself from global memory): mailbox words
                     //                     (the sums are >= 0; the sign bit carries the tag (step >> 1) & 1, slot = step & 1)
   int *fbuf;        // [kCW][32]           far frames of the rows of the current tile
   int *prog;        // [kCW]               progress counters of the chain warps (events)
@@ -325,13 +326,15 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
   double hv = 0.0;                               // cw == 0: lane cj holds the handed sum of column cj
   int known = 0;                                 // cw > 0: last progress value seen of the warp above
   const int evbase = q * kEv;
-  unsigned long long *hand_w = reinterpret_cast<unsigned long long *>(sm.hand) + ((ustep & 1) * kCW + cw) * 32;
-  const unsigned long long *hand_r = hand_w - 32;
+  unsigned long long *hand_r = reinterpret_cast<unsigned long long *>(sm.hand) + ((ustep & 1) * (kCW + 1) + cw) * 32;
+  unsigned long long *hand_w = hand_r + 32;
   const unsigned long long tagbit = (unsigned long long)((ustep >> 1) & 1) << 63;
   if (cw == 0) {
     // handed in from the previous pass (or the seed) through global memory; fetched one block ahead
     Fh = Fh_pre;
     hv = hv_pre;
+    st_relaxed_u64(hand_r + lane, (unsigned long long)__double_as_longlong(hv) | tagbit);   // same path as the other chunks
+    __syncwarp();
     int pn = p, qn = q + 1;
     if (qn >= g.NBv) { pn = p + 1; qn = 0; }
     if (pn < g.NP) {
@@ -395,7 +398,16 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
       a[4] = fma(md, u2.x, a[4]); a[5] = fma(md, u2.y, a[5]); a[6] = fma(md, u3.x, a[6]); a[7] = fma(md, u3.y, a[7]);
     }
     if (swdbg) sgA += clock64() - sa0;
-    unsigned long long zraw = (cw > 0) ? ld_relaxed_u64(hand_r + 8 * G) : 0ull;
+    unsigned long long zraw = ld_relaxed_u64(hand_r + 8 * G);
+    // far sums (in the tile frame) and emission weights of the group: off the column-to-column dependency path
+    double fd[8];
+    int ewd[8];
+#pragma unroll
+    for (int K = 0; K < 8; K++) {
+      const int jj = BETA ? 31 - (8 * G + K) : 8 * G + K;
+      fd[K] = (double)mrow[jj] * xs;
+      ewd[K] = __float_as_int(iow[jj]);
+    }
 #pragma unroll
     for (int K = 0; K < 8; K++) {
       const int cj = 8 * G + K;
@@ -405,19 +417,13 @@ __device__ __forceinline__ void chain_phase1(const Geo &g, const Smem &sm, const
         if (to_pass) passd[((size_t)((p + 1) & 1) * g.NB + q) * 32 + cj] = a[K];
         else st_relaxed_u64(hand_w + cj, (unsigned long long)__double_as_longlong(a[K]) | tagbit);
       }
-      // what the row above hands to this column (lane 0: from the chunk above / the previous pass)
-      double z;
-      if (cw == 0) {
-        z = __shfl_sync(0xffffffffu, hv, cj) * hs;
-      } else {
-        while ((zraw ^ tagbit) >> 63) zraw = ld_relaxed_u64(hand_r + cj);
-        z = __longlong_as_double((long long)(zraw & 0x7fffffffffffffffull)) * hs;
-        if (K < 7) zraw = ld_relaxed_u64(hand_r + cj + 1);     // usually already there: the chunk above runs ahead
-      }
+      // what the row above hands to this column (lane 0 uses it)
+      while ((zraw ^ tagbit) >> 63) zraw = ld_relaxed_u64(hand_r + cj);
+      const double z = __longlong_as_double((long long)(zraw & 0x7fffffffffffffffull)) * hs;
+      if (K < 7) zraw = ld_relaxed_u64(hand_r + cj + 1);       // usually already there: the chunk above runs ahead
       double rm = __shfl_up_sync(0xffffffffu, a[K], 1);
       if (lane == 0) rm = z;
-      const double tot = fma((double)mrow[jj], xs, rm);
-      const double m = tot * __hiloint2double(__float_as_int(iow[jj]), 0);   // emission weight: 0 outside the lattice
+      const double m = (fd[K] + rm) * __hiloint2double(ewd[K], 0);   // emission weight: 0 outside the lattice
       const int mhi = __double2hiint(m);
       mrow[jj] = __int_as_float(mhi);                  // outgoing mass, 21 significant bits, frame Ft
       maxhi = max(maxhi, mhi);
@@ -670,7 +676,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
     *reinterpret_cast<uint4 *>(aop + (size_t)(x >> 3) * (g.Mr >> 7) * 16384 + (size_t)(x & 7) * 2048) = make_uint4(0u, 0u, 0u, 0u);
   for (int x = threadIdx.x; x < g.NB * 32; x += kThreads) passd[x] = 0.0;                             // parity 0
   for (int x = threadIdx.x; x < g.NB; x += kThreads) passf[x] = kNegBig;
-  for (int x = threadIdx.x; x < 2 * kCW * 32; x += kThreads)          // mailboxes: tag 1 = nothing posted for steps 0, 1
+  for (int x = threadIdx.x; x < 2 * (kCW + 1) * 32; x += kThreads)    // mailboxes: tag 1 = nothing posted for steps 0, 1
     reinterpret_cast<unsigned long long *>(sm.hand)[x] = 1ull << 63;
   if (threadIdx.x < kStages) { mbar_init(sm.full + threadIdx.x, 1); mbar_init(sm.empty + threadIdx.x, 1); }
   if (threadIdx.x < kTSlots) { mbar_init(sm.tfull + threadIdx.x, 1); mbar_init(sm.tempty + threadIdx.x, 4); }
@@ -998,7 +1004,7 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
   sm.ring = p;                               p += (size_t)kStages * kStageBytes;
   sm.afresh = p;                             p += 32768;
   sm.ut = reinterpret_cast<double *>(p);     p += 8192;
-  sm.hand = reinterpret_cast<double *>(p);   p += 2 * kCW * 32 * sizeof(double);
+  sm.hand = reinterpret_cast<double *>(p);   p += 2 * (kCW + 1) * 32 * sizeof(double);
   sm.full = reinterpret_cast<uint64_t *>(p);   p += kStages * 8;
   sm.empty = reinterpret_cast<uint64_t *>(p);  p += kStages * 8;
   sm.tfull = reinterpret_cast<uint64_t *>(p);  p += kTSlots * 8;
@@ -1023,7 +1029,7 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
 size_t dp4_smem_bytes(int M, int L) {
   using namespace dp4;
   TileLayout lay = TileLayout::make(L, M);
-  return (size_t)kStages * kStageBytes + 32768 + 8192 + 2 * kCW * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 +
+  return (size_t)kStages * kStageBytes + 32768 + 8192 + 2 * (kCW + 1) * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 +
          (size_t)3 * kCW * kTileF * 4 + 2 * kCW * 32 * 4 + kCW * 32 * 4 + 2 * kCW * 4 + (size_t)257 * lay.NB * 2 + 64;
 }
 

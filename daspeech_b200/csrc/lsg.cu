@@ -13,6 +13,8 @@
 //
 // Rows that do not fit the register path (V not a multiple of the vector width, huge V, fp64) take a
 // streaming three-pass kernel whose 2nd/3rd pass hit L2.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dagb200 {
@@ -142,6 +144,166 @@ lsg_fwd_reg_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int6
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// forward, TMA-staged: one CTA walks kLsgGroup consecutive vertices (rows) of one utterance.  Rows are bulk-copied
+// (cp.async.bulk, one 16-byte-aligned row per copy) into a ring of kLsgStages shared-memory stages by one thread,
+// so the next rows are in flight while the current one is reduced -- no registers are tied up by loads in flight.
+// The S target logits are gathered from the staged row (no second trip to L2), and the results of the group are
+// written together: with the transposed [B,S,L] result layout that is one 32-byte segment per target instead of
+// eight scattered 4-byte stores.
+constexpr int kLsgGroup = 8;
+constexpr int kLsgStages = 3;
+
+__device__ __forceinline__ uint32_t lsg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lsg_mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(lsg_smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void lsg_load_row(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lsg_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(lsg_smem_u32(dst)), "l"(src), "r"(bytes), "r"(lsg_smem_u32(bar)) : "memory");
+}
+
+template <typename T, int NV, bool GRAD>
+__global__ void __launch_bounds__(kLsgThreads)
+lsg_fwd_tma_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int64_t isb, int64_t isl, int64_t iss,
+                   float *__restrict__ out, int64_t osb, int64_t osl, int64_t oss, int L, int V, int S, int groups) {
+  using VT = VecTraits<T>;
+  constexpr int E = VT::kElems;
+  extern __shared__ __align__(128) unsigned char lsg_smem[];
+  const uint32_t rowbytes = (uint32_t)V * sizeof(T);
+  unsigned char *stages = lsg_smem;                                            // [kLsgStages][rowbytes]
+  float *outb = reinterpret_cast<float *>(lsg_smem + (size_t)kLsgStages * rowbytes);   // [S][kLsgGroup + 1]
+  int *idxs = reinterpret_cast<int *>(outb + (size_t)S * (kLsgGroup + 1));     // [S]
+  float *red = reinterpret_cast<float *>(idxs + S);                            // [16]
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + 16);                     // [kLsgStages]
+
+  const int b = blockIdx.x / groups, l0 = (blockIdx.x % groups) * kLsgGroup;
+  const int nrows = min(kLsgGroup, L - l0);
+  T *xg = logits + ((int64_t)b * L + l0) * (int64_t)V;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLsgStages; i++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsg_smem_u32(full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int r = 0; r < min(kLsgStages, nrows); r++)
+      lsg_load_row(stages + (size_t)r * rowbytes, xg + (int64_t)r * V, rowbytes, full + r);
+  }
+  const bool shared_idx = (isl == 0);
+  if (shared_idx) {
+    const int64_t *ib = idx + b * isb;
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) idxs[s] = (int)ib[s * iss];
+  }
+  __syncthreads();
+  const int nvec = V / E;
+
+  for (int r = 0; r < nrows; r++) {
+    const int st = r % kLsgStages;
+    const T *xs = reinterpret_cast<const T *>(stages + (size_t)st * rowbytes);
+    if (!shared_idx) {
+      const int64_t *ib = idx + b * isb + (l0 + r) * isl;
+      for (int s = threadIdx.x; s < S; s += kLsgThreads) idxs[s] = (int)ib[s * iss];
+      __syncthreads();
+    }
+    lsg_mbar_wait(full + st, (r / kLsgStages) & 1);
+    float v[NV][E];
+    float tmax = neg_inf_f();
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int c = k * kLsgThreads + threadIdx.x;
+      if (c < nvec) {
+        const uint4 u = reinterpret_cast<const uint4 *>(xs)[c];
+        VT::unpack(u, v[k]);
+#pragma unroll
+        for (int e = 0; e < E; e++) tmax = fmaxf(tmax, v[k][e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) v[k][e] = neg_inf_f();
+      }
+    }
+    // raw target logits from the staged row (outb doubles as their parking place)
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) outb[s * (kLsgGroup + 1) + r] = VT::to_float(xs[idxs[s]]);
+    const float rmax = block_allreduce<true>(tmax, red);
+    // every thread is past its reads of this stage: refill it with the row kLsgStages ahead
+    if (threadIdx.x == 0 && r + kLsgStages < nrows) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      lsg_load_row(stages + (size_t)st * rowbytes, xg + (int64_t)(r + kLsgStages) * V, rowbytes, full + st);
+    }
+    float tsum = 0.f;
+    const float moff = (rmax == neg_inf_f()) ? 0.f : rmax;
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+#pragma unroll
+      for (int e = 0; e < E; e++) { v[k][e] = __expf(v[k][e] - moff); tsum += v[k][e]; }
+    const float rsum = block_allreduce<false>(tsum, red + 8);
+    const float lsum = __logf(rsum);
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) {
+      float *o = outb + s * (kLsgGroup + 1) + r;
+      *o = (*o - rmax) - lsum;
+    }
+    if (GRAD) {
+      const float inv = __fdividef(1.f, rsum);
+      T *x = xg + (int64_t)r * V;
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        const int c = k * kLsgThreads + threadIdx.x;
+        if (c < nvec) {
+#pragma unroll
+          for (int e = 0; e < E; e++) v[k][e] *= inv;
+          reinterpret_cast<uint4 *>(x)[c] = VT::pack(v[k]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // results of the group
+  float *ob = out + b * osb + (int64_t)l0 * osl;
+  const bool vec = (osl == 1) && nrows == kLsgGroup && ((oss & 3) == 0) && ((osb & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec) {
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) {
+      const float *o = outb + s * (kLsgGroup + 1);
+      float4 *dst = reinterpret_cast<float4 *>(ob + s * oss);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  } else if (oss == 1) {
+    for (int r = 0; r < nrows; r++)
+      for (int s = threadIdx.x; s < S; s += kLsgThreads) ob[r * osl + s] = outb[s * (kLsgGroup + 1) + r];
+  } else {
+    for (int x = threadIdx.x; x < S * nrows; x += kLsgThreads) {
+      const int s = x / nrows, r = x % nrows;
+      ob[r * osl + s * oss] = outb[s * (kLsgGroup + 1) + r];
+    }
+  }
+}
+
+static size_t lsg_fwd_tma_smem(size_t rowbytes, int S) {
+  return (size_t)kLsgStages * rowbytes + (size_t)S * (kLsgGroup + 1) * 4 + (size_t)S * 4 + 16 * 4 + kLsgStages * 8 + 16;
+}
+
+template <typename T, int NV>
+static int launch_fwd_tma(T *logits, const int64_t *idx, int64_t isb, int64_t isl, int64_t iss, float *out,
+                          int64_t osb, int64_t osl, int64_t oss, int B, int L, int V, int S, bool grad,
+                          cudaStream_t st) {
+  const size_t smem = lsg_fwd_tma_smem((size_t)V * sizeof(T), S);
+  const int groups = (L + kLsgGroup - 1) / kLsgGroup;
+  const unsigned grid = (unsigned)((int64_t)B * groups);
+  if (grad) {
+    cudaFuncSetAttribute(lsg_fwd_tma_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    lsg_fwd_tma_kernel<T, NV, true><<<grid, kLsgThreads, smem, st>>>(logits, idx, isb, isl, iss, out, osb, osl, oss, L, V, S, groups);
+  } else {
+    cudaFuncSetAttribute(lsg_fwd_tma_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    lsg_fwd_tma_kernel<T, NV, false><<<grid, kLsgThreads, smem, st>>>(logits, idx, isb, isl, iss, out, osb, osl, oss, L, V, S, groups);
+  }
+  DAGB200_CHECK_LAUNCH("lsg_fwd_tma_kernel");
+  return 0;
+}
+
 // forward, streaming fallback (any V / alignment); T2 = compute type
 template <typename T, typename C, bool GRAD>
 __global__ void __launch_bounds__(kLsgThreads)
@@ -253,6 +415,150 @@ lsg_bwd_vec_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int64
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// backward, TMA-staged, same organisation as lsg_fwd_tma_kernel: a CTA owns kLsgGroup consecutive vertices of one
+// utterance; the incoming gradients of the group are fetched once (32-byte segments of the transposed [B,S,L]
+// buffer), the probability rows stream through a ring of bulk copies, every row is scaled into an fp32 copy in
+// shared memory (double-buffered), takes the scatter as shared-memory atomics and is written back once.
+template <typename T, int NV, int STAGES>
+__global__ void __launch_bounds__(kLsgThreads)
+lsg_bwd_tma_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int64_t isb, int64_t isl, int64_t iss,
+                   const float *__restrict__ gout, int64_t gsb, int64_t gsl, int64_t gss, int L, int V, int S, int groups) {
+  using VT = VecTraits<T>;
+  constexpr int E = VT::kElems;
+  extern __shared__ __align__(128) unsigned char lsg_smem[];
+  const uint32_t rowbytes = (uint32_t)V * sizeof(T);
+  unsigned char *stages = lsg_smem;                                            // [STAGES][rowbytes]
+  float *rowf = reinterpret_cast<float *>(lsg_smem + (size_t)STAGES * rowbytes);       // [2][V]
+  float *gbuf = rowf + (size_t)2 * V;                                          // [S][kLsgGroup + 1]
+  int *idxs = reinterpret_cast<int *>(gbuf + (size_t)S * (kLsgGroup + 1));     // [S]
+  float *red = reinterpret_cast<float *>(idxs + S);                            // [8 warps][kLsgGroup] + [kLsgGroup]
+  uint64_t *full = reinterpret_cast<uint64_t *>(red + 9 * kLsgGroup);          // [STAGES]
+
+  const int b = blockIdx.x / groups, l0 = (blockIdx.x % groups) * kLsgGroup;
+  const int nrows = min(kLsgGroup, L - l0);
+  T *xg = probs + ((int64_t)b * L + l0) * (int64_t)V;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsg_smem_u32(full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int r = 0; r < min(STAGES, nrows); r++)
+      lsg_load_row(stages + (size_t)r * rowbytes, xg + (int64_t)r * V, rowbytes, full + r);
+  }
+  const bool shared_idx = (isl == 0);
+  if (shared_idx) {
+    const int64_t *ib = idx + b * isb;
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) idxs[s] = (int)ib[s * iss];
+  }
+  // incoming gradients of the group and their per-vertex sums
+  const float *gb = gout + b * gsb + (int64_t)l0 * gsl;
+  const bool vec = (gsl == 1) && nrows == kLsgGroup && ((gss & 3) == 0) && ((gsb & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+  float part[kLsgGroup];
+#pragma unroll
+  for (int r = 0; r < kLsgGroup; r++) part[r] = 0.f;
+  for (int s = threadIdx.x; s < S; s += kLsgThreads) {
+    float g[kLsgGroup];
+    if (vec) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(gb + s * gss));
+      const float4 c = __ldg(reinterpret_cast<const float4 *>(gb + s * gss) + 1);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = c.x; g[5] = c.y; g[6] = c.z; g[7] = c.w;
+    } else {
+#pragma unroll
+      for (int r = 0; r < kLsgGroup; r++) g[r] = (r < nrows) ? gb[r * gsl + s * gss] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kLsgGroup; r++) { gbuf[s * (kLsgGroup + 1) + r] = g[r]; part[r] += g[r]; }
+  }
+#pragma unroll
+  for (int r = 0; r < kLsgGroup; r++) part[r] = warp_sum(part[r]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int r = 0; r < kLsgGroup; r++) red[(threadIdx.x >> 5) * kLsgGroup + r] = part[r];
+  }
+  __syncthreads();
+  if (threadIdx.x < kLsgGroup) {
+    float t = 0.f;
+    for (int w = 0; w < kLsgThreads / 32; w++) t += red[w * kLsgGroup + threadIdx.x];
+    // the reference casts -sum to the logits dtype before the multiply (dag_loss.py:294)
+    red[8 * kLsgGroup + threadIdx.x] = VT::to_float(VT::from_float(-t));
+  }
+  __syncthreads();
+  const int nvec = V / E;
+
+  for (int r = 0; r < nrows; r++) {
+    const int st = r % STAGES;
+    const T *xs = reinterpret_cast<const T *>(stages + (size_t)st * rowbytes);
+    float *rf = rowf + (size_t)(r & 1) * V;
+    if (!shared_idx) {
+      const int64_t *ib = idx + b * isb + (l0 + r) * isl;
+      for (int s = threadIdx.x; s < S; s += kLsgThreads) idxs[s] = (int)ib[s * iss];   // ordered by the barrier below
+    }
+    const float neg = red[8 * kLsgGroup + r];
+    lsg_mbar_wait(full + st, (r / STAGES) & 1);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int c = k * kLsgThreads + threadIdx.x;
+      if (c < nvec) {
+        const uint4 u = reinterpret_cast<const uint4 *>(xs)[c];
+        float f[E];
+        VT::unpack(u, f);
+#pragma unroll
+        for (int e = 0; e < E; e++) f[e] = VT::to_float(VT::from_float(f[e] * neg));
+        if (E == 8) {
+          reinterpret_cast<float4 *>(rf)[2 * c] = make_float4(f[0], f[1], f[2], f[3]);
+          reinterpret_cast<float4 *>(rf)[2 * c + 1] = make_float4(f[4 % E], f[5 % E], f[6 % E], f[7 % E]);
+        } else {
+          reinterpret_cast<float4 *>(rf)[c] = make_float4(f[0], f[1], f[2], f[3]);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && r + STAGES < nrows) {   // every thread is past its reads of this stage
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      lsg_load_row(stages + (size_t)st * rowbytes, xg + (int64_t)(r + STAGES) * V, rowbytes, full + st);
+    }
+    for (int s = threadIdx.x; s < S; s += kLsgThreads)
+      atomicAdd(&rf[idxs[s]], VT::to_float(VT::from_float(gbuf[s * (kLsgGroup + 1) + r])));
+    __syncthreads();
+    T *x = xg + (int64_t)r * V;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int c = k * kLsgThreads + threadIdx.x;
+      if (c < nvec) {
+        float f[E];
+        if (E == 8) {
+          const float4 a = reinterpret_cast<const float4 *>(rf)[2 * c], d = reinterpret_cast<const float4 *>(rf)[2 * c + 1];
+          f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4 % E] = d.x; f[5 % E] = d.y; f[6 % E] = d.z; f[7 % E] = d.w;
+        } else {
+          const float4 a = reinterpret_cast<const float4 *>(rf)[c];
+          f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        }
+        reinterpret_cast<uint4 *>(x)[c] = VT::pack(f);
+      }
+    }
+  }
+}
+
+template <int STAGES> static size_t lsg_bwd_tma_smem(size_t rowbytes, int V, int S) {
+  return (size_t)STAGES * rowbytes + (size_t)2 * V * 4 + (size_t)S * (kLsgGroup + 1) * 4 + (size_t)S * 4 + 9 * kLsgGroup * 4 +
+         STAGES * 8 + 16;
+}
+
+template <typename T, int NV>
+static int launch_bwd_tma(T *probs, const int64_t *idx, int64_t isb, int64_t isl, int64_t iss, const float *gout,
+                          int64_t gsb, int64_t gsl, int64_t gss, int B, int L, int V, int S, cudaStream_t st) {
+  constexpr int STAGES = sizeof(T) == 4 ? 2 : 3;
+  const size_t smem = lsg_bwd_tma_smem<STAGES>((size_t)V * sizeof(T), V, S);
+  const int groups = (L + kLsgGroup - 1) / kLsgGroup;
+  const unsigned grid = (unsigned)((int64_t)B * groups);
+  cudaFuncSetAttribute(lsg_bwd_tma_kernel<T, NV, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  lsg_bwd_tma_kernel<T, NV, STAGES><<<grid, kLsgThreads, smem, st>>>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, L, V, S, groups);
+  DAGB200_CHECK_LAUNCH("lsg_bwd_tma_kernel");
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NV>
 static int launch_fwd_reg(T *logits, const int64_t *idx, int64_t isb, int64_t isl, int64_t iss, float *out,
@@ -276,6 +582,14 @@ static int lsg_fwd_dispatch16(T *logits, const int64_t *idx, int64_t isb, int64_
   const bool aligned = (V % E == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   const int nvec = V / E;
   const int need = (nvec + kLsgThreads - 1) / kLsgThreads;
+  // TMA-staged path: rows of <= 32 KB that keep at least two CTAs per SM resident
+  static const bool no_tma = getenv("DAGB200_LSG_NOTMA") != nullptr;
+  if (!no_tma && aligned && need <= 8 && (size_t)V * sizeof(T) <= 32768 && lsg_fwd_tma_smem((size_t)V * sizeof(T), S) <= 110 * 1024) {
+    if (need <= 1) return launch_fwd_tma<T, 1>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
+    if (need <= 2) return launch_fwd_tma<T, 2>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
+    if (need <= 4) return launch_fwd_tma<T, 4>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
+    return launch_fwd_tma<T, 8>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
+  }
   if (aligned && need <= 16 && S <= 8192) {
     if (need <= 1) return launch_fwd_reg<T, 1>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
     if (need <= 2) return launch_fwd_reg<T, 2>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
@@ -301,6 +615,15 @@ static int lsg_bwd_dispatch16(T *probs, const int64_t *idx, int64_t isb, int64_t
   const bool aligned = (V % E == 0) && ((reinterpret_cast<uintptr_t>(probs) & 15) == 0);
   const size_t smem = (size_t)(V + 16) * sizeof(float);
   if (smem > 200 * 1024) { set_error("logsoftmax_gather_backward: V=%d too large for the staged row", V); return DAGB200_ELIMIT; }
+  static const bool no_tma = getenv("DAGB200_LSG_NOTMA") != nullptr;
+  const int need = (V / E + kLsgThreads - 1) / kLsgThreads;
+  if (!no_tma && aligned && need <= 8 && (size_t)V * sizeof(T) <= 32768 &&
+      lsg_bwd_tma_smem<sizeof(T) == 4 ? 2 : 3>((size_t)V * sizeof(T), V, S) <= 110 * 1024) {
+    if (need <= 1) return launch_bwd_tma<T, 1>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+    if (need <= 2) return launch_bwd_tma<T, 2>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+    if (need <= 4) return launch_bwd_tma<T, 4>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+    return launch_bwd_tma<T, 8>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+  }
   if (aligned) {
     cudaFuncSetAttribute(lsg_bwd_vec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     lsg_bwd_vec_kernel<T><<<(unsigned)rows, kLsgThreads, smem, st>>>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, L, V, S);
