@@ -116,6 +116,50 @@ __device__ __forceinline__ void vit_group(float (&vrow)[kVB], const float *edw, 
   vit_column<CJ0 + 7>(vrow, edw, mm, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
 }
 
+// ---- value-only variants (cluster kernel): the forward sweep keeps NO back-pointers -- max is exact in any order, so
+// the lattice is bit-identical -- and the arg-max with the reference's tie-break is recomputed during the backtrace
+// for the cells on the path only (M cells instead of M x L).
+template <int CJ>
+__device__ __forceinline__ void vitv_column(float (&vrow)[kVB], const float *edw, const float (&mm)[8], float *iow,
+                                            const float *xvw, int lane, float d0v, bool rowvalid, int jbase, int t,
+                                            int O, bool &anyfin) {
+  const float ninf = neg_inf_f();
+  float n0 = ninf, n1 = ninf;      // best in-block predecessor of MY row for the next row's column CJ
+#pragma unroll
+  for (int c4 = 0; c4 < CJ; c4 += 4) {
+    const float4 e4 = *reinterpret_cast<const float4 *>(edw + CJ * kVB + c4);
+    if (c4 + 0 < CJ) n0 = fmaxf(n0, vrow[c4 + 0] + e4.x);
+    if (c4 + 1 < CJ) n1 = fmaxf(n1, vrow[c4 + 1] + e4.y);
+    if (c4 + 2 < CJ) n0 = fmaxf(n0, vrow[c4 + 2] + e4.z);
+    if (c4 + 3 < CJ) n1 = fmaxf(n1, vrow[c4 + 3] + e4.w);
+  }
+  float rv = __shfl_up_sync(0xffffffffu, fmaxf(n0, n1), 1);
+  const float zv = __shfl_sync(0xffffffffu, d0v, CJ);
+  if (lane == 0) rv = zv;
+  const float best = fmaxf(rv, xvw[CJ]);
+  const int j = jbase + CJ;
+  const bool valid = rowvalid && j >= t && j < O;
+  const float val = valid ? best + mm[CJ & 7] : ninf;
+  vrow[CJ] = val;
+  iow[CJ] = val;
+  anyfin = anyfin || (val > ninf);
+}
+template <int CJ0>
+__device__ __forceinline__ void vitv_group(float (&vrow)[kVB], const float *edw, float *iow, const float *xvw, int lane,
+                                           float d0v, bool rowvalid, int jbase, int t, int O, bool &anyfin) {
+  float mm[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) mm[k] = iow[CJ0 + k];
+  vitv_column<CJ0 + 0>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 1>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 2>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 3>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 4>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 5>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 6>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+  vitv_column<CJ0 + 7>(vrow, edw, mm, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+}
+
 __global__ void __launch_bounds__(kV2Threads, 1)
 dag_viterbi_blocked_kernel(const float *__restrict__ match, const float *__restrict__ links,
                            const int64_t *__restrict__ olen, const int64_t *__restrict__ tlen,
@@ -360,7 +404,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kV2Threads, 1)
 dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restrict__ links,
                            const int64_t *__restrict__ olen, const int64_t *__restrict__ tlen,
-                           float *lattice, uint16_t *trace, int32_t *__restrict__ path,
+                           float *lattice, int32_t *__restrict__ path,
                            unsigned char *gflags, int M, int L, int Tl, int NB, int32_t *__restrict__ status) {
   extern __shared__ __align__(16) unsigned char v2_smem[];
   const int b = blockIdx.x >> 1, rank = blockIdx.x & 1;
@@ -369,7 +413,6 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
   const int64_t latsz = (int64_t)M * L;
   const float ninf = neg_inf_f();
   float *lat = lattice + b * latsz;
-  uint16_t *trg = trace + b * latsz;
   int32_t *prow = path + (int64_t)b * L;
   const float *m = match + b * latsz;
   const float *E = links + (int64_t)b * L * Tl;
@@ -390,12 +433,10 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
   }
 
   float *s_ed, *s_xv, *s_io, *s_vs;
-  int *s_xd;
   {
     float *p = reinterpret_cast<float *>(v2_smem);
     s_ed = p;  p += kVcTpw * kVB * kVB;
     s_xv = p;  p += kVcTpw * kVB * kV2Pitch;
-    s_xd = reinterpret_cast<int *>(p);  p += kVcTpw * kVB * kV2Pitch;
     s_io = p;  p += kVcTpw * kVB * kV2Pitch;
     s_vs = p;
   }
@@ -447,9 +488,9 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
             asm volatile("cp.async.commit_group;" ::: "memory");
           }
           float *xvw = s_xv + (size_t)ts * kVB * kV2Pitch + (8 * sl) * kV2Pitch + lane;
-          int *xdw = s_xd + (size_t)ts * kVB * kV2Pitch + (8 * sl) * kV2Pitch + lane;
+          float xvr[8];                                    // running best far candidate of my 8 rows (value only)
 #pragma unroll
-          for (int rr = 0; rr < 8; rr++) { xvw[rr * kV2Pitch] = ninf; xdw[rr * kV2Pitch] = 0; }
+          for (int rr = 0; rr < 8; rr++) xvr[rr] = ninf;
           float *vsw = s_vs + (size_t)warp * 8 * kVB;
           const int s_first = c * kVB + 8 * sl;            // previous-row index of my first row
           const int qlo = max(0, J - band);
@@ -470,41 +511,20 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
               vsw[rr * kVB + lane] = (tp < nsteps) ? __ldcg(lat + (int64_t)tp * L + kVB * I + lane) : ninf;
             }
             __syncwarp();
-            const int dbase = kVB * (J - I) + lane;
-            int ord[4];
 #pragma unroll
-            for (int r4 = 0; r4 < 4; r4++) ord[r4] = (dbase - 1 - (((r4 & 1) << 1) | (r4 >> 1))) & 3;
             for (int rr = 0; rr < 8; rr++) {
-              float bv0 = ninf, bv1 = ninf, bv2 = ninf, bv3 = ninf;
-              int bi0 = 0, bi1 = 0, bi2 = 0, bi3 = 0;
+              float b0 = xvr[rr], b1 = ninf;
 #pragma unroll
               for (int c4 = 0; c4 < kVB; c4 += 4) {
                 const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
-                float x;
-                x = a4.x + ecol[c4 + 0]; if (x >= bv0) { bv0 = x; bi0 = c4 + 0; }
-                x = a4.y + ecol[c4 + 1]; if (x >= bv1) { bv1 = x; bi1 = c4 + 1; }
-                x = a4.z + ecol[c4 + 2]; if (x >= bv2) { bv2 = x; bi2 = c4 + 2; }
-                x = a4.w + ecol[c4 + 3]; if (x >= bv3) { bv3 = x; bi3 = c4 + 3; }
+                b0 = fmaxf(fmaxf(b0, a4.x + ecol[c4 + 0]), a4.y + ecol[c4 + 1]);
+                b1 = fmaxf(fmaxf(b1, a4.z + ecol[c4 + 2]), a4.w + ecol[c4 + 3]);
               }
-              const float bvs[4] = {bv0, bv1, bv2, bv3};
-              const int bis[4] = {bi0, bi1, bi2, bi3};
-              float nv = ninf; int ni = 0;
-#pragma unroll
-              for (int r4 = 0; r4 < 4; r4++) {
-                const int u = ord[r4];
-                const float v = (u == 0) ? bvs[0] : (u == 1) ? bvs[1] : (u == 2) ? bvs[2] : bvs[3];
-                const int ii = (u == 0) ? bis[0] : (u == 1) ? bis[1] : (u == 2) ? bis[2] : bis[3];
-                if (r4 == 0 || v > nv) { nv = v; ni = ii; }
-              }
-              const int nd = dbase - ni;
-              const float rv = xvw[rr * kV2Pitch];
-              const int rd = xdw[rr * kV2Pitch];
-              if (nv > rv || (nv == rv && nv > ninf && rank4(nd) <= rank4(rd))) {
-                xvw[rr * kV2Pitch] = nv;
-                xdw[rr * kV2Pitch] = nd;
-              }
+              xvr[rr] = fmaxf(b0, b1);
             }
           }
+#pragma unroll
+          for (int rr = 0; rr < 8; rr++) xvw[rr * kV2Pitch] = xvr[rr];
           asm volatile("cp.async.wait_all;" ::: "memory");
         }
       }
@@ -522,8 +542,7 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
           const float *edw = s_ed + (size_t)ts * kVB * kVB;
           float *iow = s_io + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
           const float *xvw = s_xv + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
-          int *xdw = s_xd + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
-          float d0v = ninf; int d0d = 0;
+          float d0v = ninf;
           {
             const int tp = c * kVB;   // previous-row index of the chunk's first row (written by the other CTA)
             const float pv = (jbase + lane < L) ? __ldcg(lat + (int64_t)tp * L + jbase + lane) : ninf;
@@ -533,28 +552,25 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
               for (int k = 0; k < 4; k++) {
                 const int ci = c4 + k;
                 const float x = __shfl_sync(0xffffffffu, pv, ci) + (k == 0 ? e4.x : k == 1 ? e4.y : k == 2 ? e4.z : e4.w);
-                const int delta = lane - ci;
-                if (ci < lane && better(x, delta, d0v, d0d)) { d0v = x; d0d = delta; }
+                if (ci < lane) d0v = fmaxf(d0v, x);
               }
             }
           }
           float vrow[kVB];
           bool anyfin = false;
-          vit_group<0>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
-          vit_group<8>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
-          vit_group<16>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
-          vit_group<24>(vrow, edw, iow, xvw, xdw, lane, d0v, d0d, rowvalid, jbase, t, O, anyfin);
+          vitv_group<0>(vrow, edw, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+          vitv_group<8>(vrow, edw, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+          vitv_group<16>(vrow, edw, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
+          vitv_group<24>(vrow, edw, iow, xvw, lane, d0v, rowvalid, jbase, t, O, anyfin);
           if (rowvalid) flag[t * NB + J] = anyfin ? 1 : 0;
           __syncwarp();
           const int rl = min(kVB, nsteps - c * kVB) - 1;
           const float *iot = s_io + (size_t)ts * kVB * kV2Pitch;
-          const int *trt = s_xd + (size_t)ts * kVB * kV2Pitch;
           const int j = jbase + lane;
           if (j < L) {
             for (int rr = 0; rr <= rl; rr++) {
               const int64_t off = (int64_t)(1 + c * kVB + rr) * L + j;
               lat[off] = iot[rr * kV2Pitch + lane];
-              trg[off] = (uint16_t)trt[rr * kV2Pitch + lane];
             }
           }
         }
@@ -564,27 +580,61 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
     cluster_sync_all();    // wave w is complete in both CTAs and visible to both
   }
 
-  // backtrace (dag_best_alignment.cu:178-184)
-  if (rank == 0 && threadIdx.x == 0) {
+  // backtrace (dag_best_alignment.cu:178-184) with the back-pointers recomputed on the way: for the cell (i, pos) of the
+  // path, all kV2Threads threads of CTA 0 score its candidates delta = 1 .. min(pos, Tl) -- ONE fp32 add each, as in the
+  // forward sweep -- and reduce them with the reference's order (value, then class priority, then smaller delta).
+  if (rank == 0) {
+    float *s_bv = reinterpret_cast<float *>(v2_smem);          // [warps]
+    int *s_bd = reinterpret_cast<int *>(v2_smem) + kV2Warps;   // [warps]
+    int *s_pos = s_bd + kV2Warps;                              // [1]
+    __syncthreads();
     int code = DAGB200_ST_OK;
+    int pos = O - 1;
     if (!(__ldcg(lat + (int64_t)(Tn - 1) * L + O - 1) > ninf)) {
       code = DAGB200_ST_NO_PATH;
     } else {
-      int pos = O - 1;
-      for (int i = Tn - 1; i >= 0; i--) {
-        prow[pos] = i;
-        if (i == 0) break;
-        const int d = __ldcg(trg + (int64_t)i * L + pos);
+      for (int i = Tn - 1; i >= 1; i--) {
+        if (threadIdx.x == 0) prow[pos] = i;
+        const float *prev = lat + (int64_t)(i - 1) * L;
+        const int dmax = min(pos, Tl);
+        float bv = ninf; int bd = 0;
+        for (int d = dmax - (int)threadIdx.x; d >= 1; d -= kV2Threads) {    // descending delta inside a thread
+          const int src = pos - d;
+          const float x = __ldcg(prev + src) + __ldg(E + (int64_t)src * Tl + d - 1);
+          if (better(x, d, bv, bd)) { bv = x; bd = d; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+          if (better(ov, od, bv, bd)) { bv = ov; bd = od; }
+        }
+        if (lane == 0) { s_bv[warp] = bv; s_bd[warp] = bd; }
+        __syncthreads();
+        if (warp == 0) {
+          bv = (lane < kV2Warps) ? s_bv[lane] : ninf;
+          bd = (lane < kV2Warps) ? s_bd[lane] : 0;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+            if (better(ov, od, bv, bd)) { bv = ov; bd = od; }
+          }
+          if (lane == 0) s_pos[0] = (bv > ninf) ? bd : 0;
+        }
+        __syncthreads();
+        const int d = s_pos[0];
         if (d == 0) { code = DAGB200_ST_NO_PATH; break; }
         pos -= d;
       }
+      if (code == DAGB200_ST_OK && threadIdx.x == 0) prow[pos] = 0;
     }
-    if (status) status[b] = code;
+    if (status && threadIdx.x == 0) status[b] = code;
   }
 }
 
 size_t vitc_smem_bytes() {
-  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 3 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * 8 * kVB) + 16;
+  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 2 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * 8 * kVB) + 16;
 }
 
 size_t vit2_smem_bytes(int M, int L) {
@@ -603,8 +653,8 @@ int launch_viterbi_blocked(const float *match, const float *links, const int64_t
     const size_t smemc = vitc_smem_bytes();
     cudaFuncSetAttribute(dag_viterbi_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemc);
     prof_mark(6, st);
-    dag_viterbi_cluster_kernel<<<2 * B, kV2Threads, smemc, st>>>(match, links, olen, tlen, lattice, trace, path, flags, M, L,
-                                                                Tl, NB, status);
+    dag_viterbi_cluster_kernel<<<2 * B, kV2Threads, smemc, st>>>(match, links, olen, tlen, lattice, path, flags, M, L, Tl, NB,
+                                                                status);
     DAGB200_CHECK_LAUNCH("dag_viterbi_cluster_kernel");
     prof_mark(7, st);
     return 0;
