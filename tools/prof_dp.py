@@ -13,5 +13,14 @@ for _ in range(n):
     gm, gl = k.dag_loss_backward(go, a, b, match, links, olen, tlen, 2, 2)
     if "--viterbi" in sys.argv:
         k.dag_best_alignment(match, links, olen, tlen, 1, want_alpha=False)
+if "--lsg" in sys.argv:
+    B, L, V, M = 64, 1024, 4096, 256
+    for dt in (torch.float16, torch.float32):
+        logits = (torch.randn(B, L, V, device=dev) * 2).to(dt)
+        idx = torch.randint(4, V, (B, M), device=dev).unsqueeze(1).expand(-1, L, -1)
+        gsel = torch.randn(B, M, L, device=dev).transpose(1, 2)
+        for _ in range(n):
+            k.logsoftmax_gather(logits, idx, True)
+            k.logsoftmax_gather_backward(logits, idx, gsel)
 torch.cuda.synchronize()
 print("ok", float(b[:, 0, 0].mean()))
