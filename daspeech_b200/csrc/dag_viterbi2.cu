@@ -119,9 +119,13 @@ __device__ __forceinline__ void vit_group(float (&vrow)[kVB], const float *edw, 
 // ---- value-only variants (cluster kernel): the forward sweep keeps NO back-pointers -- max is exact in any order, so
 // the lattice is bit-identical -- and the arg-max with the reference's tie-break is recomputed during the backtrace
 // for the cells on the path only (M cells instead of M x L).
+// order-preserving float <-> int32 key (an involution): lets shared-memory integer atomics take the float maximum
+__device__ __forceinline__ int f2key(float x) { const int b = __float_as_int(x); return b ^ ((b >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
 template <int CJ>
 __device__ __forceinline__ void vitv_column(float (&vrow)[kVB], const float *edw, const float (&mm)[8], float *iow,
-                                            const float *xvw, int lane, float d0v, bool rowvalid, int jbase, int t,
+                                            const int *xvw, int lane, float d0v, bool rowvalid, int jbase, int t,
                                             int O, bool &anyfin) {
   const float ninf = neg_inf_f();
   float n0 = ninf, n1 = ninf;      // best in-block predecessor of MY row for the next row's column CJ
@@ -136,7 +140,7 @@ __device__ __forceinline__ void vitv_column(float (&vrow)[kVB], const float *edw
   float rv = __shfl_up_sync(0xffffffffu, fmaxf(n0, n1), 1);
   const float zv = __shfl_sync(0xffffffffu, d0v, CJ);
   if (lane == 0) rv = zv;
-  const float best = fmaxf(rv, xvw[CJ]);
+  const float best = fmaxf(rv, key2f(xvw[CJ]));
   const int j = jbase + CJ;
   const bool valid = rowvalid && j >= t && j < O;
   const float val = valid ? best + mm[CJ & 7] : ninf;
@@ -145,7 +149,7 @@ __device__ __forceinline__ void vitv_column(float (&vrow)[kVB], const float *edw
   anyfin = anyfin || (val > ninf);
 }
 template <int CJ0>
-__device__ __forceinline__ void vitv_group(float (&vrow)[kVB], const float *edw, float *iow, const float *xvw, int lane,
+__device__ __forceinline__ void vitv_group(float (&vrow)[kVB], const float *edw, float *iow, const int *xvw, int lane,
                                            float d0v, bool rowvalid, int jbase, int t, int O, bool &anyfin) {
   float mm[8];
 #pragma unroll
@@ -432,13 +436,14 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
     return;
   }
 
-  float *s_ed, *s_xv, *s_io, *s_vs;
+  float *s_ed, *s_io, *s_vs;
+  int *s_xk;     // [tiles][32][pitch] best far candidate per (row, column) as an order-preserving key
   {
     float *p = reinterpret_cast<float *>(v2_smem);
     s_ed = p;  p += kVcTpw * kVB * kVB;
-    s_xv = p;  p += kVcTpw * kVB * kV2Pitch;
+    s_xk = reinterpret_cast<int *>(p);  p += kVcTpw * kVB * kV2Pitch;
     s_io = p;  p += kVcTpw * kVB * kV2Pitch;
-    s_vs = p;
+    s_vs = p;    // [warps][32][32] previous-row values of a unit's source block
   }
   const int NBv = (O + kVB - 1) / kVB;
   const int nsteps = Tn - 1;
@@ -467,66 +472,84 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
     const int c_lo = max(0, w - NBv + 1), c_hi = min(NCv - 1, w);
     const int c_first = c_lo + ((c_lo ^ rank) & 1);          // my chunks: parity = rank
     for (int cb = c_first; cb <= c_hi; cb += 2 * kVcTpw) {
-      // ======================= far phase: lanes = destination columns, 8 rows per warp =======================
+      // ======================= staging: diagonal transition blocks and emissions of the batch's tiles ==========
       {
         const int ts = warp >> 2, sl = warp & 3;
         const int c = cb + 2 * ts;
         if (c <= c_hi) {
           const int J = w - c;
           const int j = kVB * J + lane;
-          {
-            float *edw = s_ed + (size_t)ts * kVB * kVB;
-            float *iow = s_io + (size_t)ts * kVB * kV2Pitch;
-            for (int rr = sl; rr < kVB; rr += 4) {
-              const int i = kVB * J + rr, k = lane - rr - 1;
-              if (k >= 0 && k < Tl && i < O && j < O) cp_async_f32_v(edw + lane * kVB + rr, E + (int64_t)i * Tl + k);
-              else edw[lane * kVB + rr] = ninf;
-              const int s = c * kVB + rr;
-              if (s < nsteps && j < L) cp_async_f32_v(iow + rr * kV2Pitch + lane, m + (int64_t)(1 + s) * L + j);
-              else iow[rr * kV2Pitch + lane] = ninf;
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
+          float *edw = s_ed + (size_t)ts * kVB * kVB;
+          float *iow = s_io + (size_t)ts * kVB * kV2Pitch;
+          for (int rr = sl; rr < kVB; rr += 4) {
+            const int i = kVB * J + rr, k = lane - rr - 1;
+            if (k >= 0 && k < Tl && i < O && j < O) cp_async_f32_v(edw + lane * kVB + rr, E + (int64_t)i * Tl + k);
+            else edw[lane * kVB + rr] = ninf;
+            const int s = c * kVB + rr;
+            if (s < nsteps && j < L) cp_async_f32_v(iow + rr * kV2Pitch + lane, m + (int64_t)(1 + s) * L + j);
+            else iow[rr * kV2Pitch + lane] = ninf;
           }
-          float *xvw = s_xv + (size_t)ts * kVB * kV2Pitch + (8 * sl) * kV2Pitch + lane;
-          float xvr[8];                                    // running best far candidate of my 8 rows (value only)
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          int *xk = s_xk + (size_t)ts * kVB * kV2Pitch + (8 * sl) * kV2Pitch + lane;
 #pragma unroll
-          for (int rr = 0; rr < 8; rr++) xvr[rr] = ninf;
-          float *vsw = s_vs + (size_t)warp * 8 * kVB;
-          const int s_first = c * kVB + 8 * sl;            // previous-row index of my first row
-          const int qlo = max(0, J - band);
-          for (int I = qlo; I < J; I++) {
-            bool any = false;
-            if (lane < 8 && s_first + lane < nsteps) any = __ldcg(flag + (s_first + lane) * NB + I) != 0;
-            if (!__any_sync(0xffffffffu, any)) continue;
-            float ecol[kVB];
-#pragma unroll
-            for (int ii = 0; ii < kVB; ii++) {
-              const int i = kVB * I + ii, k = j - i - 1;
-              ecol[ii] = (k < Tl && j < O) ? __ldg(E + (int64_t)i * Tl + k) : ninf;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int rr = 0; rr < 8; rr++) {
-              const int tp = s_first + rr;
-              vsw[rr * kVB + lane] = (tp < nsteps) ? __ldcg(lat + (int64_t)tp * L + kVB * I + lane) : ninf;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int rr = 0; rr < 8; rr++) {
-              float b0 = xvr[rr], b1 = ninf;
-#pragma unroll
-              for (int c4 = 0; c4 < kVB; c4 += 4) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
-                b0 = fmaxf(fmaxf(b0, a4.x + ecol[c4 + 0]), a4.y + ecol[c4 + 1]);
-                b1 = fmaxf(fmaxf(b1, a4.z + ecol[c4 + 2]), a4.w + ecol[c4 + 3]);
-              }
-              xvr[rr] = fmaxf(b0, b1);
-            }
-          }
-#pragma unroll
-          for (int rr = 0; rr < 8; rr++) xvw[rr * kV2Pitch] = xvr[rr];
-          asm volatile("cp.async.wait_all;" ::: "memory");
+          for (int rr = 0; rr < 8; rr++) xk[rr * kV2Pitch] = f2key(ninf);
         }
+      }
+      __syncthreads();
+      // ======================= far phase: units = (tile, source block), dealt round-robin to the 16 warps ========
+      // A unit covers all 32 rows of its tile: the transition column of the lane's destination vertex is fetched once
+      // per unit (not once per row quarter), every warp gets the same number of units whatever the tiles' depths, and
+      // the per-(row, column) maxima of the units meet in shared memory through integer atomics on order-preserving keys.
+      {
+        int nun[kVcTpw], total = 0;
+#pragma unroll
+        for (int ts = 0; ts < kVcTpw; ts++) {
+          const int c = cb + 2 * ts, J = w - c;
+          nun[ts] = (c <= c_hi) ? J - max(0, J - band) : 0;
+          total += nun[ts];
+        }
+        float *vsw = s_vs + (size_t)warp * kVB * kVB;
+        for (int u = warp; u < total; u += kV2Warps) {
+          int ts = 0, r = u;
+#pragma unroll
+          for (int x = 0; x < kVcTpw - 1; x++)
+            if (ts == x && r >= nun[x]) { r -= nun[x]; ts = x + 1; }
+          const int c = cb + 2 * ts, J = w - c;
+          const int I = max(0, J - band) + r;
+          const int j = kVB * J + lane;
+          const int tp0 = c * kVB;                         // previous-row index of the tile's first row
+          const bool any = (tp0 + lane < nsteps) && __ldcg(flag + (tp0 + lane) * NB + I) != 0;
+          if (!__any_sync(0xffffffffu, any)) continue;
+          float ecol[kVB];
+          {
+            const int k0 = j - kVB * I - 1;                // transition index from the block's first source vertex; >= 31
+            const float *ep = E + (int64_t)(kVB * I) * Tl + k0;
+            const bool jok = j < O;
+#pragma unroll
+            for (int ii = 0; ii < kVB; ii++) ecol[ii] = (jok && k0 - ii < Tl) ? __ldg(ep + (int64_t)ii * (Tl - 1)) : ninf;
+          }
+          {
+            const float *lp = lat + (int64_t)tp0 * L + kVB * I + lane;
+#pragma unroll 8
+            for (int rr = 0; rr < kVB; rr++) vsw[rr * kVB + lane] = (tp0 + rr < nsteps) ? __ldcg(lp + (int64_t)rr * L) : ninf;
+          }
+          __syncwarp();
+          int *xk = s_xk + (size_t)ts * kVB * kV2Pitch + lane;
+#pragma unroll 4
+          for (int rr = 0; rr < kVB; rr++) {
+            float b0 = ninf, b1 = ninf;
+#pragma unroll
+            for (int c4 = 0; c4 < kVB; c4 += 4) {
+              const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
+              b0 = fmaxf(fmaxf(b0, a4.x + ecol[c4 + 0]), a4.y + ecol[c4 + 1]);
+              b1 = fmaxf(fmaxf(b1, a4.z + ecol[c4 + 2]), a4.w + ecol[c4 + 3]);
+            }
+            const float bb = fmaxf(b0, b1);
+            if (bb > ninf) atomicMax(xk + rr * kV2Pitch, f2key(bb));
+          }
+          __syncwarp();
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
       __syncthreads();
       // ======================= chain phase: lanes = rows, serial over the 32 columns =======================
@@ -541,7 +564,7 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
           const int t = 1 + s;
           const float *edw = s_ed + (size_t)ts * kVB * kVB;
           float *iow = s_io + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
-          const float *xvw = s_xv + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
+          const int *xvw = s_xk + (size_t)ts * kVB * kV2Pitch + lane * kV2Pitch;
           float d0v = ninf;
           {
             const int tp = c * kVB;   // previous-row index of the chunk's first row (written by the other CTA)
@@ -634,7 +657,7 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
 }
 
 size_t vitc_smem_bytes() {
-  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 2 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * 8 * kVB) + 16;
+  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 2 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * kVB * kVB) + 16;
 }
 
 size_t vit2_smem_bytes(int M, int L) {
