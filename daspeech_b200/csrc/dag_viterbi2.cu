@@ -443,7 +443,7 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
     s_ed = p;  p += kVcTpw * kVB * kVB;
     s_xk = reinterpret_cast<int *>(p);  p += kVcTpw * kVB * kV2Pitch;
     s_io = p;  p += kVcTpw * kVB * kV2Pitch;
-    s_vs = p;    // [warps][32][32] previous-row values of a unit's source block
+    s_vs = p;    // [warps][2][32][32] previous-row values of a unit's source block, double-buffered
   }
   const int NBv = (O + kVB - 1) / kVB;
   const int nsteps = Tn - 1;
@@ -508,46 +508,86 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
           nun[ts] = (c <= c_hi) ? J - max(0, J - band) : 0;
           total += nun[ts];
         }
-        float *vsw = s_vs + (size_t)warp * kVB * kVB;
-        for (int u = warp; u < total; u += kV2Warps) {
-          int ts = 0, r = u;
+        // few units (banded transitions, first waves): split every unit into four row quarters so that all warps work
+        const int sf = (total < kV2Warps) ? 4 : 1;
+        const int nrow = kVB / sf;
+        const int nunits = total * sf;
+        float *vs0 = s_vs + (size_t)warp * 2 * kVB * kVB;    // two slabs per warp: the next unit's rows land while this one is scored
+        const bool vec_ok = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(lat) & 15) == 0);
+        // unit -> (tile, source block, first row)
+        auto decode = [&](int u, int &ts, int &I, int &row0) {
+          int r = u / sf;
+          row0 = (u % sf) * nrow;
+          ts = 0;
 #pragma unroll
           for (int x = 0; x < kVcTpw - 1; x++)
             if (ts == x && r >= nun[x]) { r -= nun[x]; ts = x + 1; }
-          const int c = cb + 2 * ts, J = w - c;
-          const int I = max(0, J - band) + r;
-          const int j = kVB * J + lane;
-          const int tp0 = c * kVB;                         // previous-row index of the tile's first row
-          const bool any = (tp0 + lane < nsteps) && __ldcg(flag + (tp0 + lane) * NB + I) != 0;
-          if (!__any_sync(0xffffffffu, any)) continue;
-          float ecol[kVB];
-          {
-            const int k0 = j - kVB * I - 1;                // transition index from the block's first source vertex; >= 31
-            const float *ep = E + (int64_t)(kVB * I) * Tl + k0;
-            const bool jok = j < O;
-#pragma unroll
-            for (int ii = 0; ii < kVB; ii++) ecol[ii] = (jok && k0 - ii < Tl) ? __ldg(ep + (int64_t)ii * (Tl - 1)) : ninf;
-          }
-          {
-            const float *lp = lat + (int64_t)tp0 * L + kVB * I + lane;
-#pragma unroll 8
-            for (int rr = 0; rr < kVB; rr++) vsw[rr * kVB + lane] = (tp0 + rr < nsteps) ? __ldcg(lp + (int64_t)rr * L) : ninf;
-          }
-          __syncwarp();
-          int *xk = s_xk + (size_t)ts * kVB * kV2Pitch + lane;
-#pragma unroll 4
-          for (int rr = 0; rr < kVB; rr++) {
-            float b0 = ninf, b1 = ninf;
-#pragma unroll
-            for (int c4 = 0; c4 < kVB; c4 += 4) {
-              const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
-              b0 = fmaxf(fmaxf(b0, a4.x + ecol[c4 + 0]), a4.y + ecol[c4 + 1]);
-              b1 = fmaxf(fmaxf(b1, a4.z + ecol[c4 + 2]), a4.w + ecol[c4 + 3]);
+          const int J = w - (cb + 2 * ts);
+          I = max(0, J - band) + r;
+        };
+        // start fetching a unit: liveness flag of one row per lane (consumed later) and the rows themselves
+        auto stage = [&](int u, float *slab, bool &any) {
+          int ts, I, row0;
+          decode(u, ts, I, row0);
+          const int tp0 = (cb + 2 * ts) * kVB + row0;        // previous-row index of the unit's first row
+          any = (lane < nrow) && (tp0 + lane < nsteps) && __ldcg(flag + (tp0 + lane) * NB + I) != 0;
+          if (vec_ok) {
+            const int q = lane & 7;
+            for (int rr = lane >> 3; rr < nrow; rr += 4) {
+              float *dst = slab + rr * kVB + 4 * q;
+              if (tp0 + rr < nsteps) {
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(lat + (int64_t)(tp0 + rr) * L + kVB * I + 4 * q) : "memory");
+              } else {
+                *reinterpret_cast<float4 *>(dst) = make_float4(ninf, ninf, ninf, ninf);
+              }
             }
-            const float bb = fmaxf(b0, b1);
-            if (bb > ninf) atomicMax(xk + rr * kV2Pitch, f2key(bb));
+          } else {
+            const float *lp = lat + (int64_t)tp0 * L + kVB * I + lane;
+            for (int rr = 0; rr < nrow; rr++) slab[rr * kVB + lane] = (tp0 + rr < nsteps) ? __ldcg(lp + (int64_t)rr * L) : ninf;
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int buf = 0;
+        bool any_cur = false, any_next = false;
+        if (warp < nunits) stage(warp, vs0, any_cur);
+        for (int u = warp; u < nunits; u += kV2Warps) {
+          const bool more = u + kV2Warps < nunits;
+          if (more) stage(u + kV2Warps, vs0 + (buf ^ 1) * kVB * kVB, any_next);
+          if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          if (__any_sync(0xffffffffu, any_cur)) {
+            int ts, I, row0;
+            decode(u, ts, I, row0);
+            const int J = w - (cb + 2 * ts);
+            const int j = kVB * J + lane;
+            float ecol[kVB];
+            {
+              const int k0 = j - kVB * I - 1;                // transition index from the block's first source vertex; >= 31
+              const float *ep = E + (int64_t)(kVB * I) * Tl + k0;
+              const bool jok = j < O;
+#pragma unroll
+              for (int ii = 0; ii < kVB; ii++) ecol[ii] = (jok && k0 - ii < Tl) ? __ldg(ep + (int64_t)ii * (Tl - 1)) : ninf;
+            }
+            const float *vsw = vs0 + buf * kVB * kVB;
+            int *xk = s_xk + (size_t)ts * kVB * kV2Pitch + row0 * kV2Pitch + lane;
+#pragma unroll 4
+            for (int rr = 0; rr < nrow; rr++) {
+              float b0 = ninf, b1 = ninf;
+#pragma unroll
+              for (int c4 = 0; c4 < kVB; c4 += 4) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kVB + c4);
+                b0 = fmaxf(fmaxf(b0, a4.x + ecol[c4 + 0]), a4.y + ecol[c4 + 1]);
+                b1 = fmaxf(fmaxf(b1, a4.z + ecol[c4 + 2]), a4.w + ecol[c4 + 3]);
+              }
+              const float bb = fmaxf(b0, b1);
+              if (bb > ninf) atomicMax(xk + rr * kV2Pitch, f2key(bb));
+            }
           }
           __syncwarp();
+          any_cur = any_next;
+          buf ^= 1;
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
       }
@@ -657,7 +697,7 @@ dag_viterbi_cluster_kernel(const float *__restrict__ match, const float *__restr
 }
 
 size_t vitc_smem_bytes() {
-  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 2 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * kVB * kVB) + 16;
+  return sizeof(float) * ((size_t)kVcTpw * kVB * kVB + 2 * (size_t)kVcTpw * kVB * kV2Pitch + (size_t)kV2Warps * 2 * kVB * kVB) + 16;
 }
 
 size_t vit2_smem_bytes(int M, int L) {
