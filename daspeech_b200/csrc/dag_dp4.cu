@@ -184,7 +184,10 @@ struct Smem {
   uint64_t *full;   // [kStages]           ring stage filled (TMA)
   uint64_t *empty;  // [kStages]           ring stage consumed (tcgen05.commit)
   uint64_t *tfull;  // [kTSlots]           TMEM accumulator slot written (tcgen05.commit)
-  uint64_t *tempty; // [kTSlots]           TMEM accumulator slot read back (4 epilogue warps)
+  uint64_t *tempty; // [kTSlots]           (unused: replaced by `done`)
+  int *done;        // [kCW]               per epilogue warp: item count up to which its accumulator reads are complete
+                    //                     (the issuer polls it only when its cached minimum is too small for the slot it
+                    //                     wants to overwrite -- an mbarrier try-wait per item cost ~90 cycles on the issue path)
   uint64_t *ubar;   // [1]
   uint32_t *tmem;   // TMEM base address
 };
@@ -557,6 +560,8 @@ struct Issuer {
   int n;             // items whose MMAs have been issued
   bool dbg, logq;
   int logbase;
+  int st, stpar;     // ring stage of the next item and its mbarrier parity
+  int cmin;          // cached minimum of Smem::done over the epilogue warps
   long long t_full, t_tempty, t_p1, t_p2;
 };
 __device__ __forceinline__ uint32_t elect_one() {
@@ -568,11 +573,19 @@ __device__ __forceinline__ uint32_t elect_one() {
 // UTCHMMA issue needs no per-instruction vector->uniform transfer); one elected lane issues.
 __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t tmem_base, uint32_t ring_u32, uint32_t afresh_u32,
                                            bool from_afresh, int mt) {
-  const int st = is.n % kStages, pp = is.n % kTSlots, k = is.n / kTSlots;
+  const int st = is.st, pp = is.n % kTSlots;
   long long c0 = is.dbg ? clock64() : 0;
-  mbar_wait(sm.full + st, (is.n / kStages) & 1);
+  mbar_wait(sm.full + st, is.stpar);
   long long c1 = is.dbg ? clock64() : 0;
-  if (k >= 1) mbar_wait(sm.tempty + pp, (k - 1) & 1);
+  {
+    // slot pp was last used by item n - kTSlots: every epilogue warp must be past that item (a warp counts the items of
+    // the other 128-row tile as soon as it skips them)
+    const int need = is.n - kTSlots + 1;
+    while (is.cmin < need) {
+      const volatile int *dn = sm.done;
+      is.cmin = min(min(min(dn[0], dn[1]), min(dn[2], dn[3])), min(min(dn[4], dn[5]), min(dn[6], dn[7])));
+    }
+  }
   long long c2 = is.dbg ? clock64() : 0;
   if (is.dbg) { is.t_full += c1 - c0; is.t_tempty += c2 - c1; }
   tc_fence_after();
@@ -587,10 +600,11 @@ __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t 
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < 2; ks++) {
-      const uint64_t ahi = dA | (uint64_t)((a0 + ks * akstep) & 0x3fff);
-      const uint64_t alo = dA | (uint64_t)((a0 + aplane + ks * akstep) & 0x3fff);
-      const uint64_t bhi = dB | (uint64_t)((b0 + ks * 64) & 0x3fff);
-      const uint64_t blo = dB | (uint64_t)((b0 + 128 + ks * 64) & 0x3fff);
+      // shared-memory addresses are < 256 KB: the 14-bit field never carries
+      const uint64_t ahi = dA | (uint64_t)(a0 + ks * akstep);
+      const uint64_t alo = dA | (uint64_t)(a0 + aplane + ks * akstep);
+      const uint64_t bhi = dB | (uint64_t)(b0 + ks * 64);
+      const uint64_t blo = dB | (uint64_t)(b0 + 128 + ks * 64);
       umma_f16(d, ahi, bhi, ks > 0 ? 1u : 0u);
       umma_f16(d, alo, bhi, 1u);
       umma_f16(d, ahi, blo, 1u);
@@ -604,6 +618,7 @@ __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t 
     if (i >= 0 && i < 64) { g_ev[0][i][0] = c0; g_ev[0][i][1] = c1; g_ev[0][i][2] = c2; g_ev[0][i][3] = clock64(); }
   }
   is.n++;
+  if (++is.st == kStages) { is.st = 0; is.stpar ^= 1; }
 }
 
 // epilogue warp state: far sums of my row for the current destination block, online maximum of the source frames
@@ -619,7 +634,10 @@ __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_b
   const int pp = e.n % kTSlots, k = e.n / kTSlots;
   const int li = e.n - e.logbase;
   e.n++;
-  if (!mine) return;
+  if (!mine) {
+    if ((threadIdx.x & 31) == 0) *reinterpret_cast<volatile int *>(sm.done + (threadIdx.x >> 5) - kCW) = e.n;
+    return;
+  }
   const bool lg = logrow >= 0 && li >= 0 && li < 64;
   if (lg) g_ev[logrow][li][0] = clock64();
   mbar_wait(sm.tfull + pp, k & 1);
@@ -629,7 +647,7 @@ __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_b
   tmem_ld32(tmem_base + pp * 32 + ((uint32_t)(quarter * 32) << 16), v);
   tc_fence_before();
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(sm.tempty + pp);
+  if ((threadIdx.x & 31) == 0) *reinterpret_cast<volatile int *>(sm.done + (threadIdx.x >> 5) - kCW) = e.n;   // reads of items < e.n complete
   if (lg) g_ev[logrow][li][2] = clock64();
   if (Fs > kNegBig) {
     if (Fs > e.F) {   // the new source block sets the frame: acc = acc * 2^(F - Fs) + v  (the scale is 0 when acc is empty)
@@ -678,6 +696,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   for (int x = threadIdx.x; x < g.NB; x += kThreads) passf[x] = kNegBig;
   for (int x = threadIdx.x; x < 2 * (kCW + 1) * 32; x += kThreads)    // mailboxes: tag 1 = nothing posted for steps 0, 1
     reinterpret_cast<unsigned long long *>(sm.hand)[x] = 1ull << 63;
+  if (threadIdx.x < kCW) sm.done[threadIdx.x] = 0;
   if (threadIdx.x < kStages) { mbar_init(sm.full + threadIdx.x, 1); mbar_init(sm.empty + threadIdx.x, 1); }
   if (threadIdx.x < kTSlots) { mbar_init(sm.tfull + threadIdx.x, 1); mbar_init(sm.tempty + threadIdx.x, 4); }
   if (threadIdx.x == 0) mbar_init(sm.ubar, 1);
@@ -796,6 +815,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
     is.dbg = dbg && blockIdx.x == 0 && lane == 0;
     is.t_full = is.t_tempty = is.t_p1 = is.t_p2 = 0;
     is.logq = false; is.logbase = 0;
+    is.st = 0; is.stpar = 0; is.cmin = 0;
     // everything that shapes the item sequence as warp-uniform values
     const uint32_t ring_u32 = __shfl_sync(0xffffffffu, smem_u32(sm.ring), 0);
     const uint32_t afresh_u32 = __shfl_sync(0xffffffffu, smem_u32(sm.afresh), 0);
@@ -1011,6 +1031,7 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
   sm.tempty = reinterpret_cast<uint64_t *>(p); p += kTSlots * 8;
   sm.ubar = reinterpret_cast<uint64_t *>(p);   p += 2 * 8;
   sm.tmem = reinterpret_cast<uint32_t *>(p);   p += 16;
+  sm.done = reinterpret_cast<int *>(p);        p += kCW * 4;
   sm.xbuf = reinterpret_cast<float *>(p);    p += (size_t)kCW * kTileF * 4;
   sm.io = reinterpret_cast<float *>(p);      p += (size_t)2 * kCW * kTileF * 4;
   sm.rmxs = reinterpret_cast<float *>(p);    p += 2 * kCW * 32 * 4;
@@ -1029,7 +1050,7 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
 size_t dp4_smem_bytes(int M, int L) {
   using namespace dp4;
   TileLayout lay = TileLayout::make(L, M);
-  return (size_t)kStages * kStageBytes + 32768 + 8192 + 2 * (kCW + 1) * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 +
+  return (size_t)kStages * kStageBytes + 32768 + 8192 + 2 * (kCW + 1) * 32 * 8 + (2 * kStages + 2 * kTSlots + 2) * 8 + 16 + kCW * 4 +
          (size_t)3 * kCW * kTileF * 4 + 2 * kCW * 32 * 4 + kCW * 32 * 4 + 2 * kCW * 4 + (size_t)257 * lay.NB * 2 + 64;
 }
 
