@@ -10,7 +10,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
-constexpr int kM = 128, kN = 32, kK = 64;          // K = 64 -> 4 MMAs of K = 16
+constexpr int kM = 128, kK = 64;                   // K = 64 -> 4 MMAs of K = 16; N is a template parameter
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,6 +51,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!ok);
 }
 
+template <int kN>
 __global__ void __launch_bounds__(128, 1)
 probe(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ B, float *__restrict__ D, int reps,
       long long *cyc) {
@@ -73,7 +74,7 @@ probe(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ B, 
   // make the generic-proxy writes of the operands visible to the async (tensor-core) proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -136,10 +137,11 @@ probe(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ B, 
   if (tid == 0) *cyc = t1 - t0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
-int main() {
+template <int kN>
+int run() {
   const int nA = kM * kK, nB = kN * kK;
   __nv_bfloat16 *hA = new __nv_bfloat16[nA], *hB = new __nv_bfloat16[nB];
   float *fA = new float[nA], *fB = new float[nB];
@@ -150,27 +152,34 @@ int main() {
   cudaMalloc(&dA, nA * 2); cudaMalloc(&dB, nB * 2); cudaMalloc(&dD, kM * kN * 4); cudaMalloc(&dc, 32);
   cudaMemcpy(dA, hA, nA * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, nB * 2, cudaMemcpyHostToDevice);
   cudaMemset(dD, 0, kM * kN * 4);
-  probe<<<1, 128>>>(dA, dB, dD, 1, dc);
+  probe<kN><<<1, 128>>>(dA, dB, dD, 1, dc);
   cudaError_t e = cudaDeviceSynchronize();
-  printf("launch: %s\n", cudaGetErrorString(e));
+  printf("N = %d launch: %s\n", kN, cudaGetErrorString(e));
   if (e != cudaSuccess) return 1;
   float *hD = new float[kM * kN];
   cudaMemcpy(hD, dD, kM * kN * 4, cudaMemcpyDeviceToHost);
   double maxerr = 0, maxref = 0;
   for (int r = 0; r < kM; r++)
-    for (int n = 0; n < kN; n++) {
+    for (int n = 0; n < 32; n++) {     // the epilogue of the probe reads back the first 32 columns
       double s = 0;
       for (int k = 0; k < kK; k++) s += (double)fA[r * kK + k] * fB[n * kK + k];
       maxerr = fmax(maxerr, fabs(s - hD[r * kN + n])); maxref = fmax(maxref, fabs(s));
     }
-  printf("D[0][0..3] = %f %f %f %f ; max |err| = %.3e (max |ref| = %.3f) -> %s\n", hD[0], hD[1], hD[2], hD[3], maxerr, maxref,
-         maxerr < 1e-3 * maxref ? "OK" : "MISMATCH");
-  for (int reps : {100, 1000}) {
-    probe<<<1, 128>>>(dA, dB, dD, reps, dc);
+  printf("  max |err| = %.3e (max |ref| = %.3f) -> %s\n", maxerr, maxref, maxerr < 1e-3 * maxref ? "OK" : "MISMATCH");
+  for (int reps : {1000}) {
+    probe<kN><<<1, 128>>>(dA, dB, dD, reps, dc);
     cudaDeviceSynchronize();
     long long c[3]; cudaMemcpy(c, dc, 24, cudaMemcpyDeviceToHost);
-    printf("reps %d: %.1f cycles per (4 x MMA M128 N32 K16 + commit + wait); 96 MMAs back to back: issue %.1f cycles each, %.1f cycles each until complete\n",
-           reps, (double)c[0] / reps, c[1] / 96.0, c[2] / 96.0);
+    printf("  reps %d: %.1f cycles per (4 x MMA M128 N%d K16 + commit + wait); 96 MMAs back to back: issue %.1f cycles each, %.1f cycles each until complete\n",
+           reps, (double)c[0] / reps, kN, c[1] / 96.0, c[2] / 96.0);
   }
   return 0;
+}
+
+int main() {
+  int rc = 0;
+  rc |= run<32>();
+  rc |= run<64>();
+  rc |= run<128>();
+  return rc;
 }
