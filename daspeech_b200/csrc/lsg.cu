@@ -541,6 +541,165 @@ lsg_bwd_tma_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int64
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// backward for 16-bit rows with a shared (stride-0) index row: the scatter is applied while the row is in registers.
+// The S targets of the utterance are bucketed once per CTA by the 16-byte vector they fall into (counting sort in
+// shared memory); per row a thread scales its vectors, adds the gradients of the targets in its buckets (usually none)
+// and writes -- no fp32 copy of the row in shared memory, one barrier per row, twice the CTAs per SM.
+template <typename T, int NV>
+__global__ void __launch_bounds__(kLsgThreads)
+lsg_bwd_tma16_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int64_t isb, int64_t iss,
+                     const float *__restrict__ gout, int64_t gsb, int64_t gsl, int64_t gss, int L, int V, int S, int groups) {
+  using VT = VecTraits<T>;
+  constexpr int E = VT::kElems;
+  constexpr int STAGES = kLsgStages;
+  extern __shared__ __align__(128) unsigned char lsg_smem[];
+  const uint32_t rowbytes = (uint32_t)V * sizeof(T);
+  const int nvec = V / E;
+  unsigned char *stages = lsg_smem;                                            // [STAGES][rowbytes]
+  uint64_t *full = reinterpret_cast<uint64_t *>(lsg_smem + (size_t)STAGES * rowbytes);  // [STAGES] (+ pad to 32 bytes)
+  float *gbuf = reinterpret_cast<float *>(full + 4);                           // [S][kLsgGroup + 1]
+  int *idxs = reinterpret_cast<int *>(gbuf + (size_t)S * (kLsgGroup + 1));     // [S]
+  int *boff = idxs + S;                                                        // [nvec + 1] bucket offsets
+  int *bfill = boff + nvec + 1;                                                // [nvec]     fill cursors
+  int *blist = bfill + nvec;                                                   // [S]        targets sorted by bucket
+  float *red = reinterpret_cast<float *>(blist + S);                           // [8][kLsgGroup] + [kLsgGroup]
+
+  const int b = blockIdx.x / groups, l0 = (blockIdx.x % groups) * kLsgGroup;
+  const int nrows = min(kLsgGroup, L - l0);
+  T *xg = probs + ((int64_t)b * L + l0) * (int64_t)V;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lsg_smem_u32(full + i)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int r = 0; r < min(STAGES, nrows); r++)
+      lsg_load_row(stages + (size_t)r * rowbytes, xg + (int64_t)r * V, rowbytes, full + r);
+  }
+  {
+    const int64_t *ib = idx + b * isb;
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) idxs[s] = (int)ib[s * iss];
+    for (int c = threadIdx.x; c <= nvec; c += kLsgThreads) boff[c] = 0;
+    for (int c = threadIdx.x; c < nvec; c += kLsgThreads) bfill[c] = 0;
+  }
+  // incoming gradients of the group and their per-vertex sums
+  const float *gb = gout + b * gsb + (int64_t)l0 * gsl;
+  const bool vec = (gsl == 1) && nrows == kLsgGroup && ((gss & 3) == 0) && ((gsb & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+  float part[kLsgGroup];
+#pragma unroll
+  for (int r = 0; r < kLsgGroup; r++) part[r] = 0.f;
+  for (int s = threadIdx.x; s < S; s += kLsgThreads) {
+    float g[kLsgGroup];
+    if (vec) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(gb + s * gss));
+      const float4 c = __ldg(reinterpret_cast<const float4 *>(gb + s * gss) + 1);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = c.x; g[5] = c.y; g[6] = c.z; g[7] = c.w;
+    } else {
+#pragma unroll
+      for (int r = 0; r < kLsgGroup; r++) g[r] = (r < nrows) ? gb[r * gsl + s * gss] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < kLsgGroup; r++) {
+      part[r] += g[r];
+      gbuf[s * (kLsgGroup + 1) + r] = VT::to_float(VT::from_float(g[r]));   // the reference scatters the gradient in the row's dtype
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kLsgGroup; r++) part[r] = warp_sum(part[r]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int r = 0; r < kLsgGroup; r++) red[(threadIdx.x >> 5) * kLsgGroup + r] = part[r];
+  }
+  __syncthreads();
+  if (threadIdx.x < kLsgGroup) {
+    float t = 0.f;
+    for (int w = 0; w < kLsgThreads / 32; w++) t += red[w * kLsgGroup + threadIdx.x];
+    red[8 * kLsgGroup + threadIdx.x] = VT::to_float(VT::from_float(-t));   // dag_loss.py:294: -sum in the row's dtype
+  }
+  // counting sort of the targets by vector: histogram, exclusive scan, fill
+  for (int s = threadIdx.x; s < S; s += kLsgThreads) atomicAdd(&boff[idxs[s] / E + 1], 1);
+  __syncthreads();
+  {
+    // inclusive scan of boff[1 .. nvec] by one warp (nvec <= 2048: 64 entries per lane at most)
+    if (threadIdx.x < 32) {
+      const int per = (nvec + 31) / 32;
+      const int lo = 1 + threadIdx.x * per, hi = min(nvec + 1, lo + per);
+      int sum = 0;
+      for (int c = lo; c < hi; c++) sum += boff[c];
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)threadIdx.x >= o) incl += v;
+      }
+      int run = incl - sum;
+      for (int c = lo; c < hi; c++) { run += boff[c]; boff[c] = run; }
+    }
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += kLsgThreads) {
+    const int c = idxs[s] / E;
+    blist[boff[c] + atomicAdd(&bfill[c], 1)] = s;
+  }
+  __syncthreads();
+
+  for (int r = 0; r < nrows; r++) {
+    const int st = r % STAGES;
+    const T *xs = reinterpret_cast<const T *>(stages + (size_t)st * rowbytes);
+    const float neg = red[8 * kLsgGroup + r];
+    lsg_mbar_wait(full + st, (r / STAGES) & 1);
+    float f[NV][E];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int c = k * kLsgThreads + threadIdx.x;
+      if (c < nvec) {
+        const uint4 u = reinterpret_cast<const uint4 *>(xs)[c];
+        VT::unpack(u, f[k]);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && r + STAGES < nrows) {   // every thread is past its reads of this stage
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      lsg_load_row(stages + (size_t)st * rowbytes, xg + (int64_t)(r + STAGES) * V, rowbytes, full + st);
+    }
+    T *x = xg + (int64_t)r * V;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      const int c = k * kLsgThreads + threadIdx.x;
+      if (c < nvec) {
+#pragma unroll
+        for (int e = 0; e < E; e++) f[k][e] = VT::to_float(VT::from_float(f[k][e] * neg));
+        for (int q = boff[c]; q < boff[c + 1]; q++) {
+          const int s = blist[q];
+          const int col = idxs[s] - c * E;
+          const float gv = gbuf[s * (kLsgGroup + 1) + r];
+#pragma unroll
+          for (int e = 0; e < E; e++) f[k][e] += (e == col) ? gv : 0.f;
+        }
+        reinterpret_cast<uint4 *>(x)[c] = VT::pack(f[k]);
+      }
+    }
+  }
+}
+
+static size_t lsg_bwd_tma16_smem(size_t rowbytes, int nvec, int S) {
+  return (size_t)kLsgStages * rowbytes + (size_t)S * (kLsgGroup + 1) * 4 + (size_t)S * 4 + (size_t)(2 * nvec + 1) * 4 + (size_t)S * 4 +
+         9 * kLsgGroup * 4 + 32 + 16;
+}
+
+template <typename T, int NV>
+static int launch_bwd_tma16(T *probs, const int64_t *idx, int64_t isb, int64_t iss, const float *gout, int64_t gsb,
+                            int64_t gsl, int64_t gss, int B, int L, int V, int S, cudaStream_t st) {
+  const size_t smem = lsg_bwd_tma16_smem((size_t)V * sizeof(T), V / VecTraits<T>::kElems, S);
+  const int groups = (L + kLsgGroup - 1) / kLsgGroup;
+  const unsigned grid = (unsigned)((int64_t)B * groups);
+  cudaFuncSetAttribute(lsg_bwd_tma16_kernel<T, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  lsg_bwd_tma16_kernel<T, NV><<<grid, kLsgThreads, smem, st>>>(probs, idx, isb, iss, gout, gsb, gsl, gss, L, V, S, groups);
+  DAGB200_CHECK_LAUNCH("lsg_bwd_tma16_kernel");
+  return 0;
+}
+
 template <int STAGES> static size_t lsg_bwd_tma_smem(size_t rowbytes, int V, int S) {
   return (size_t)STAGES * rowbytes + (size_t)2 * V * 4 + (size_t)S * (kLsgGroup + 1) * 4 + (size_t)S * 4 + 9 * kLsgGroup * 4 +
          STAGES * 8 + 16;
@@ -617,6 +776,13 @@ static int lsg_bwd_dispatch16(T *probs, const int64_t *idx, int64_t isb, int64_t
   if (smem > 200 * 1024) { set_error("logsoftmax_gather_backward: V=%d too large for the staged row", V); return DAGB200_ELIMIT; }
   static const bool no_tma = getenv("DAGB200_LSG_NOTMA") != nullptr;
   const int need = (V / E + kLsgThreads - 1) / kLsgThreads;
+  // 16-bit rows with the criterion's expanded (stride-0) index view: scatter applied in registers
+  if (!no_tma && aligned && sizeof(T) == 2 && isl == 0 && need <= 4 && V / E <= 2048 &&
+      lsg_bwd_tma16_smem((size_t)V * sizeof(T), V / E, S) <= 72 * 1024) {
+    if (need <= 1) return launch_bwd_tma16<T, 1>(probs, idx, isb, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+    if (need <= 2) return launch_bwd_tma16<T, 2>(probs, idx, isb, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+    return launch_bwd_tma16<T, 4>(probs, idx, isb, iss, gout, gsb, gsl, gss, B, L, V, S, st);
+  }
   if (!no_tma && aligned && need <= 8 && (size_t)V * sizeof(T) <= 32768 &&
       lsg_bwd_tma_smem<sizeof(T) == 4 ? 2 : 3>((size_t)V * sizeof(T), V, S) <= 110 * 1024) {
     if (need <= 1) return launch_bwd_tma<T, 1>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, B, L, V, S, st);

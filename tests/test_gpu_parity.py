@@ -282,6 +282,31 @@ def test_logsoftmax_gather_against_golden(name, dtype):
     assert torch.allclose(sel2, sel.detach())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shared_idx", [True, False])
+def test_logsoftmax_gather_duplicates_and_ragged_groups(dtype, shared_idx):
+    """Targets with many duplicates (the scatter must accumulate, dag_loss.py:295), a vertex count that is not a
+    multiple of the kernels' 8-row groups, expanded (stride-0) and genuinely strided index tensors."""
+    torch.manual_seed(5)
+    B, L, V, S = 3, 21, 1024, 40
+    x0 = (torch.randn(B, L, V, device=DEV) * 2).to(dtype)
+    tg = torch.randint(0, 16, (B, S), device=DEV) * 8 + torch.randint(0, 3, (B, S), device=DEV)   # few distinct ids
+    if shared_idx:
+        idx = tg.unsqueeze(1).expand(-1, L, -1)
+    else:
+        idx = (tg.unsqueeze(1) + torch.arange(L, device=DEV).view(1, L, 1)) % V
+    w = torch.randn(B, L, S, device=DEV)
+    xr = x0.detach().double().requires_grad_()
+    sel_ref = torch.log_softmax(xr, -1).gather(-1, idx)
+    gref = torch.autograd.grad((sel_ref * w.double()).sum(), [xr])[0]
+    leaf = x0.clone().requires_grad_()
+    _, sel = ops.dag_logsoftmax_gather_inplace(leaf * 1, idx)
+    assert torch.allclose(sel.double(), sel_ref.detach(), rtol=2e-5, atol=2e-4)
+    grad = torch.autograd.grad((sel * w).sum(), [leaf])[0]
+    gtol = {torch.float32: 1e-4, torch.float16: 2e-2, torch.bfloat16: 6e-2}[dtype]
+    assert relerr(grad.double().cpu().numpy(), gref.cpu().numpy()) <= gtol
+
+
 def test_logsoftmax_gather_layouts_and_errors():
     x = torch.randn(2, 5, 64, device=DEV)
     idx_full = torch.randint(0, 64, (2, 5, 3), device=DEV)   # genuinely strided (non-expanded) indices
