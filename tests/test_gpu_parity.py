@@ -307,6 +307,31 @@ def test_logsoftmax_gather_duplicates_and_ragged_groups(dtype, shared_idx):
     assert relerr(grad.double().cpu().numpy(), gref.cpu().numpy()) <= gtol
 
 
+def test_device_prefetcher_overlapped_inputs_give_identical_results():
+    """daspeech_b200.prefetch.DevicePrefetcher: inputs copied on a side stream one step ahead; every step must see
+    exactly its own batch (different data per step) and produce the loss of the plain, serial path."""
+    from daspeech_b200.prefetch import DevicePrefetcher
+    host = []
+    want = []
+    for s in range(4):
+        match, links, olen, tlen = oracle.make_lattice(3, 40, 12, 39, seed=100 + s, ragged=True)
+        tens = (torch.tensor(match).pin_memory(), torch.tensor(links).pin_memory(), torch.tensor(olen).pin_memory(),
+                torch.tensor(tlen).pin_memory())
+        host.append(tens)
+        dev_t = [t.to(DEV) for t in tens]
+        dev_t[0].requires_grad_()     # same code path as below: with a gradient the loss is read from beta[0,0]
+        want.append(ops.dag_loss(*dev_t).detach().cpu())
+    got = []
+    for m, lk, ol, tl in DevicePrefetcher(iter(host), torch.device(DEV)):
+        m.requires_grad_()
+        loss = ops.dag_loss(m, lk, ol, tl)
+        loss.sum().backward()
+        got.append(loss.detach().cpu())
+    assert len(got) == 4
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
 def test_logsoftmax_gather_layouts_and_errors():
     x = torch.randn(2, 5, 64, device=DEV)
     idx_full = torch.randint(0, 64, (2, 5, 3), device=DEV)   # genuinely strided (non-expanded) indices
