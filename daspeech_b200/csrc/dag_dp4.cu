@@ -542,7 +542,10 @@ __device__ __forceinline__ void producer_run(Producer &pr, const Geo &g, const S
     if (it.p > cur_p) break;
     if (!last && it.qs > safe_q) break;
     const int st = pr.issued % kStages;
-    if (pr.issued >= kStages) mbar_wait(sm.empty + st, ((pr.issued / kStages) - 1) & 1);
+    if (pr.issued >= kStages) {       // the stage was last used by item issued - kStages: its MMAs must be complete
+      const int prev = pr.issued - kStages;
+      mbar_wait(sm.tfull + prev % kTSlots, (prev / kTSlots) & 1);
+    }
     unsigned char *dst = sm.ring + (size_t)st * kStageBytes;
     const int Jd = BETA ? g.NBv - 1 - it.J : it.J;           // vertex-block index of the destination (sweep J)
     const int Js = BETA ? g.NBv - 1 - it.qs : it.qs;         // ... of the source
@@ -597,6 +600,8 @@ __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t 
   const uint32_t a0 = (from_afresh ? afresh_u32 + mt * 2048 : stage) >> 4;
   const uint32_t aplane = (from_afresh ? 16384u : 8192u) >> 4, akstep = (from_afresh ? 8192u : 4096u) >> 4;
   const uint32_t b0 = (stage + 16384) >> 4;
+  const long long c3 = is.dbg ? clock64() : 0;
+  long long c4 = 0, c5 = 0;
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < 2; ks++) {
@@ -609,13 +614,17 @@ __device__ __forceinline__ void issuer_mma(Issuer &is, const Smem &sm, uint32_t 
       umma_f16(d, alo, bhi, 1u);
       umma_f16(d, ahi, blo, 1u);
     }
-    umma_commit(sm.empty + st);     // the stage may be refilled once these MMAs have read it
-    umma_commit(sm.tfull + pp);     // ... and the accumulator slot is complete
+    if (is.dbg) c4 = clock64();
+    // ONE commit per item: "accumulator slot complete" also tells the producer that the item's ring stage has been read
+    // (it waits on the slot barrier of the item that used the stage last)
+    umma_commit(sm.tfull + pp);
+    if (is.dbg) c5 = clock64();
   }
   __syncwarp();
   if (is.dbg && is.logq) {
     const int i = is.n - is.logbase;
-    if (i >= 0 && i < 64) { g_ev[0][i][0] = c0; g_ev[0][i][1] = c1; g_ev[0][i][2] = c2; g_ev[0][i][3] = clock64(); }
+    if (i >= 0 && i < 64) { g_ev[0][i][0] = c0; g_ev[0][i][1] = c1; g_ev[0][i][2] = c2; g_ev[0][i][3] = clock64();
+                            g_ev[3][i][1] = c3; g_ev[3][i][2] = c4; g_ev[3][i][3] = c5; }
   }
   is.n++;
   if (++is.st == kStages) { is.st = 0; is.stpar ^= 1; }
@@ -668,7 +677,8 @@ __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_b
 template <bool BETA>
 __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict__ lat, unsigned char *__restrict__ ws,
                              const TileLayout &lay, const Smem &sm, int O, int Tn, int M, int L, int Tl, int dbgi) {
-  const bool dbg = (dbgi & 0xff) != 0;
+  const bool dbg = (dbgi & 1) != 0;        // bit 0: all role timers and item logs; bit 1: only the per-block barrier timeline
+  const bool tlm = (dbgi & 3) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float ninf = neg_inf_f();
   Geo g;
@@ -758,7 +768,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   auto cta_sync = [] { asm volatile("bar.sync 0;" ::: "memory"); };
   long long t_b1 = 0, t_b2 = 0;
   // debug timeline: arrival / release clocks of six observer threads at both barriers of every block (CTA 0, alpha)
-  const int tl_role = (!dbg || BETA || blockIdx.x != 0 || lane != 0) ? -1
+  const int tl_role = (!tlm || BETA || blockIdx.x != 0 || lane != 0) ? -1
                       : (warp == 0 ? 0 : warp == 7 ? 1 : warp == 8 ? 2 : warp == 15 ? 3 : warp == kIssuerWarp ? 4 : warp == kProducerWarp ? 5 : -1);
   auto cta_sync1 = [&](int q) {
     if (tl_role >= 0 && q < 32) g_tl[tl_role][q][0] = clock64();
@@ -972,12 +982,21 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   }
   tc_fence_before();
   __syncthreads();
+  if (tlm && !dbg && !BETA && blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("[dp4 light timeline alpha] per block: issuer's phase-1 length (barrier to barrier), arrivals at barrier 1 relative to its release: chain0 chain7 epi0 epi7 issuer producer; phase-2 length\n");
+    for (int q = 1; q < min(g.NBv, 32); q++) {
+      const long long rel1 = g_tl[4][q][1], st1 = g_tl[4][q - 1][3];
+      printf("  q %2d  p1 %6lld | %6lld %6lld %6lld %6lld %6lld %6lld | p2 %6lld\n", q, rel1 - st1, g_tl[0][q][0] - rel1, g_tl[1][q][0] - rel1,
+             g_tl[2][q][0] - rel1, g_tl[3][q][0] - rel1, g_tl[4][q][0] - rel1, g_tl[5][q][0] - rel1, g_tl[4][q][3] - rel1);
+    }
+  }
   if (dbg && !BETA && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long z0 = g_ev[3][0][0];
     printf("[dp4 items of block %d] issuer: start, full ok, tmem-empty ok, issued | epilogue (owner warp): start wait, tfull ok, ld done+released, fma done\n", g_evq);
     for (int i = 0; i < 56; i++) {
       const int r = (i & 1) ? 2 : 1;
-      printf("  item %2d  %6lld %6lld %6lld %6lld | %6lld %6lld %6lld %6lld\n", i, g_ev[0][i][0] - z0, g_ev[0][i][1] - z0, g_ev[0][i][2] - z0, g_ev[0][i][3] - z0,
+      printf("  item %2d  %6lld %6lld %6lld [pre-issue %6lld mma-issued %6lld committed %6lld] %6lld | %6lld %6lld %6lld %6lld\n", i, g_ev[0][i][0] - z0, g_ev[0][i][1] - z0, g_ev[0][i][2] - z0,
+             g_ev[3][i][1] - z0, g_ev[3][i][2] - z0, g_ev[3][i][3] - z0, g_ev[0][i][3] - z0,
              g_ev[r][i][0] - z0, g_ev[r][i][1] - z0, g_ev[r][i][2] - z0, g_ev[r][i][3] - z0);
     }
     printf("[dp4 epilogue warps 0 / 7 per block] prepass start, prepass end, takes start, takes end (relative to chain 0 leaving barrier 2 of the previous block)\n");
