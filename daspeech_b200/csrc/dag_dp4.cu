@@ -674,11 +674,12 @@ __device__ __forceinline__ void epi_take(Epi &e, const Smem &sm, uint32_t tmem_b
 
 // ---------------------------------------------------------------------------------------------------------
 // One direction of one utterance.
-template <bool BETA>
+template <bool BETA, bool DBG>
 __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict__ lat, unsigned char *__restrict__ ws,
                              const TileLayout &lay, const Smem &sm, int O, int Tn, int M, int L, int Tl, int dbgi) {
-  const bool dbg = (dbgi & 1) != 0;        // bit 0: all role timers and item logs; bit 1: only the per-block barrier timeline
-  const bool tlm = (dbgi & 3) != 0;
+  // DBG is a compile-time switch: the production kernel carries none of the timers below
+  const bool dbg = DBG && (dbgi & 1) != 0;  // bit 0: all role timers and item logs; bit 1: only the per-block barrier timeline
+  const bool tlm = DBG && (dbgi & 3) != 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float ninf = neg_inf_f();
   Geo g;
@@ -1018,11 +1019,11 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
   if (warp == kIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__restrict__ olen,
-                              const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
-                              unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
-                              int32_t *__restrict__ status, int dbg) {
+template <bool DBG>
+__device__ __forceinline__ void alpha_beta_body(const float *__restrict__ match, const int64_t *__restrict__ olen,
+                                                const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
+                                                unsigned char *__restrict__ ws, int M, int L, int Tl, const TileLayout &lay,
+                                                int32_t *__restrict__ status, int dbg) {
   extern __shared__ __align__(128) unsigned char dp4_smem[];
   const int b = blockIdx.x;
   const bool is_beta = blockIdx.y == 1;
@@ -1060,8 +1061,24 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
   sm.rmtab = reinterpret_cast<short *>(p);
   const float *m = match + b * latsz;
   unsigned char *wsb = ws + (size_t)b * lay.sample_bytes;
-  if (is_beta) colmajor_dir<true>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg);
-  else colmajor_dir<false>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg);
+  if (is_beta) colmajor_dir<true, DBG>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg);
+  else colmajor_dir<false, DBG>(m, dst, wsb, lay, sm, O, Tn, M, L, Tl, dbg);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__restrict__ olen,
+                              const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
+                              unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
+                              int32_t *__restrict__ status) {
+  alpha_beta_body<false>(match, olen, tlen, alpha, beta, ws, M, L, Tl, lay, status, 0);
+}
+// the same kernel with the in-kernel timers / timelines compiled in (DAGB200_DP4_DEBUG != 0)
+__global__ void __launch_bounds__(kThreads, 1)
+dag_alpha_beta_tcgen05_debug_kernel(const float *__restrict__ match, const int64_t *__restrict__ olen,
+                                    const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
+                                    unsigned char *__restrict__ ws, int M, int L, int Tl, TileLayout lay,
+                                    int32_t *__restrict__ status, int dbg) {
+  alpha_beta_body<true>(match, olen, tlen, alpha, beta, ws, M, L, Tl, lay, status, dbg);
 }
 
 }  // namespace dp4
@@ -1090,9 +1107,15 @@ int launch_alpha_beta_tcgen05(const float *match, const float *links, const int6
   dim3 grid(B, grad ? 2 : 1);
   const size_t smem = dp4_smem_bytes(M, L);
   static const int dbg = getenv("DAGB200_DP4_DEBUG") ? atoi(getenv("DAGB200_DP4_DEBUG")) : 0;
-  cudaFuncSetAttribute(dag_alpha_beta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dag_alpha_beta_tcgen05_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
-                                                              M, L, Tl, lay, status, dbg);
+  if (dbg) {
+    cudaFuncSetAttribute(dag_alpha_beta_tcgen05_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dag_alpha_beta_tcgen05_debug_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
+                                                                      M, L, Tl, lay, status, dbg);
+  } else {
+    cudaFuncSetAttribute(dag_alpha_beta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dag_alpha_beta_tcgen05_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
+                                                                M, L, Tl, lay, status);
+  }
   DAGB200_CHECK_LAUNCH("dag_alpha_beta_tcgen05_kernel");
   prof_mark(2, st);
   return 0;

@@ -120,6 +120,40 @@ probe(const __nv_bfloat16 *__restrict__ A, const __nv_bfloat16 *__restrict__ B, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) { cyc[1] = t3 - t2; cyc[2] = clock64() - t2; }
   }
+  // issuer-style loop (as in dag_dp4.cu): the whole warp 0 iterates; per item one elected lane issues 6 MMAs + ONE commit,
+  // the warp reconverges; commits go to a ring of 8 mbarriers that nobody waits on except every 8th item
+  __shared__ __align__(8) uint64_t ring[8];
+  if (reps > 1) {
+    if (tid < 8) mbar_init(&ring[tid], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      const long long t4 = clock64();
+      for (int it = 0; it < 256; it++) {
+        const int sl = it & 7;
+        if (it >= 8) mbar_wait(&ring[sl], ((it >> 3) - 1) & 1);      // slot reuse: item it - 8 complete
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+        if (pred) {
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            const int ks = m & 1;
+            const uint64_t ad = make_desc(smem_u32(sa) + ks * 2 * kM * 16, kM * 16, 128);
+            const uint64_t bd = make_desc(smem_u32(sb) + ks * 2 * kN * 16, kN * 16, 128);
+            mma_f16_ss(tmem + (uint32_t)(sl & 3) * 32, ad, bd, idesc, m > 0 ? 1u : 0u);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&ring[sl])) : "memory");
+        }
+        __syncwarp();
+      }
+      const long long t5 = clock64();
+      for (int sl = 0; sl < 8; sl++) mbar_wait(&ring[sl], 1);         // 256 items: 32 per slot -> last phase parity 1
+      if (tid == 0) { cyc[3] = t5 - t4; }
+    }
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   // epilogue: thread = row (warp w reads TMEM lanes 32w .. 32w+31), 32 columns
   uint32_t v[32];
   const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
@@ -149,7 +183,7 @@ int run() {
   for (int i = 0; i < nA; i++) { hA[i] = __float2bfloat16((rand() % 2001 - 1000) / 1000.f); fA[i] = __bfloat162float(hA[i]); }
   for (int i = 0; i < nB; i++) { hB[i] = __float2bfloat16((rand() % 2001 - 1000) / 1000.f); fB[i] = __bfloat162float(hB[i]); }
   __nv_bfloat16 *dA, *dB; float *dD; long long *dc;
-  cudaMalloc(&dA, nA * 2); cudaMalloc(&dB, nB * 2); cudaMalloc(&dD, kM * kN * 4); cudaMalloc(&dc, 32);
+  cudaMalloc(&dA, nA * 2); cudaMalloc(&dB, nB * 2); cudaMalloc(&dD, kM * kN * 4); cudaMalloc(&dc, 64);
   cudaMemcpy(dA, hA, nA * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, nB * 2, cudaMemcpyHostToDevice);
   cudaMemset(dD, 0, kM * kN * 4);
   probe<kN><<<1, 128>>>(dA, dB, dD, 1, dc);
@@ -169,9 +203,10 @@ int run() {
   for (int reps : {1000}) {
     probe<kN><<<1, 128>>>(dA, dB, dD, reps, dc);
     cudaDeviceSynchronize();
-    long long c[3]; cudaMemcpy(c, dc, 24, cudaMemcpyDeviceToHost);
+    long long c[4]; cudaMemcpy(c, dc, 32, cudaMemcpyDeviceToHost);
     printf("  reps %d: %.1f cycles per (4 x MMA M128 N%d K16 + commit + wait); 96 MMAs back to back: issue %.1f cycles each, %.1f cycles each until complete\n",
            reps, (double)c[0] / reps, kN, c[1] / 96.0, c[2] / 96.0);
+    printf("  issuer-style loop (warp-wide, elect, 6 MMAs + 1 commit per item, 8-slot ring): %.1f cycles per item\n", c[3] / 256.0);
   }
   return 0;
 }
