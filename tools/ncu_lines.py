@@ -18,7 +18,7 @@ for l in open(disp):
     if m:
         ins.append((cur, m.group(2)))
 rows = list(csv.reader(open(csvp)))
-hdr = rows[1]; data = rows[2:]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) > 2]
 ix = {h: i for i, h in enumerate(hdr)}
 assert len(data) == len(ins), (len(data), len(ins))
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
