@@ -114,6 +114,7 @@ SHAPES = [
     (2, 352, 300, 351, True, 0.0),   # more than 256 target rows: two passes of the column-major recurrences
     (1, 640, 530, 639, False, 0.0),  # three passes, 17 row chunks (odd split between the Viterbi cluster CTAs)
     (2, 320, 290, 40, True, 0.1),    # two passes, banded transitions, forced emissions
+    (1, 2080, 24, 2079, False, 0.0), # 65 vertex blocks: beyond the shared memory of the tcgen05 / mma.sync recurrences (dp2 fallback)
 ]
 
 
@@ -284,11 +285,13 @@ def test_logsoftmax_gather_against_golden(name, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shared_idx", [True, False])
-def test_logsoftmax_gather_duplicates_and_ragged_groups(dtype, shared_idx):
+@pytest.mark.parametrize("VS", [(1024, 40), (4104, 300)])
+def test_logsoftmax_gather_duplicates_and_ragged_groups(dtype, shared_idx, VS):
     """Targets with many duplicates (the scatter must accumulate, dag_loss.py:295), a vertex count that is not a
     multiple of the kernels' 8-row groups, expanded (stride-0) and genuinely strided index tensors."""
     torch.manual_seed(5)
-    B, L, V, S = 3, 21, 1024, 40
+    B, L = 3, 21
+    V, S = VS
     x0 = (torch.randn(B, L, V, device=DEV) * 2).to(dtype)
     tg = torch.randint(0, 16, (B, S), device=DEV) * 8 + torch.randint(0, 3, (B, S), device=DEV)   # few distinct ids
     if shared_idx:
