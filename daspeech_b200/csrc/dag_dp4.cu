@@ -936,6 +936,7 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
         const int epr = (edbg && !BETA && q < 32) ? (ew == 0 ? 0 : 1) : -1;
         if (epr >= 0) g_ep[epr][q][0] = e0;
         float rmx_next = 0.f;
+        bool converted = false;
         if (active && have) rmx_next = epi_prepass_stage<BETA>(g, sm, match, g_rmax, p, q + 1, ew, lane);   // raw emissions of the next block
         if (edbg) t_post += clock64() - e0;
         long long e2 = edbg ? clock64() : 0;
@@ -953,7 +954,13 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
           for (int j = 0; j < 32; j++) e.acc[j] = 0.f;
           e.F = kNegBig;
           if (epr >= 0) g_ep[epr][q][2] = clock64();
-          for (int qs = max(0, J - g.band); qs <= J - 2; qs++)
+          for (int qs = max(0, J - g.band); qs <= J - 2; qs++) {
+            // the weights of the next block are converted in the middle of the takes (their raw emissions have landed by
+            // then, and the tail of the phase stays short); phases with few items convert after the loop
+            if (!converted && qs == max(0, J - g.band) + 6) {
+              if (active) epi_prepass_convert<BETA>(g, sm, rmx_next, p, q + 1, ew, lane);
+              converted = true;
+            }
             for (int mt = 0; mt < ntl; mt++) {
               const bool mine = (mt == mymt);
               const int Fs = (mine && tile_on && rowvalid) ? rm_load(sm.rmtab + (ew * 32 + lane) * g.NB + qs) : kNegBig;
@@ -962,12 +969,13 @@ __device__ void colmajor_dir(const float *__restrict__ match, float *__restrict_
               epi_take(e, sm, tmem_base, quarter, Fs, mine, logrow);
               if (logrow >= 0) g_ev[logrow][e.n - 1 - e.logbase < 64 ? e.n - 1 - e.logbase : 63][3] = clock64();
             }
+          }
         }
         if (edbg) t_take += clock64() - e2;
         if (epr >= 0) g_ep[epr][q][3] = clock64();
         {
           const long long e3 = edbg ? clock64() : 0;
-          if (active && have) epi_prepass_convert<BETA>(g, sm, rmx_next, p, q + 1, ew, lane);                // ... into weights
+          if (active && have && !converted) epi_prepass_convert<BETA>(g, sm, rmx_next, p, q + 1, ew, lane);  // ... into weights
           if (edbg) t_pre += clock64() - e3;
         }
         cta_sync1(q);
