@@ -83,3 +83,13 @@ def test_torch_gather_matches_golden():
     idx = torch.tensor(g["targets"]).unsqueeze(1).expand(-1, L, -1)
     same, sel = ops.torch_dag_logsoftmax_gather_inplace(x, idx)
     assert same is x and np.allclose(sel.numpy(), g["selected"], rtol=1e-5, atol=1e-6)
+
+
+def test_prefetcher_has_no_cpu_path_and_numa_binding_is_best_effort():
+    """daspeech_b200.prefetch: the prefetcher is device plumbing only (no CPU fallback); the NUMA helper never raises."""
+    import pytest
+    from daspeech_b200 import prefetch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="needs a CUDA device"):
+            prefetch.DevicePrefetcher(iter([(torch.zeros(2),)]), torch.device("cpu"))
+    assert prefetch.bind_host_to_gpu(0) in (True, False)
