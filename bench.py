@@ -418,6 +418,21 @@ def main():
                                                   "bwd_frac": by_b / ms_b / 1e6 / peak_gbs}
             del logits, idx, gsel
 
+        # next row of the path: the S2S criterion's alignment posterior, fused vs the criterion's torch ops
+        from daspeech_b200.posterior import dag_posterior
+        a2, b2_ = k.dag_loss(match, links, olen, tlen, True, 1)
+        def torch_posterior():
+            sc = (a2 + b2_ - ops.logsumexp_keepdim(a2 + b2_, -1)).exp()
+            sc.masked_fill_(torch.isnan(sc), 0)
+            return sc
+        ms_t = timeit(torch_posterior)
+        for name, dt, esz in (("fp32", torch.float32, 4), ("fp16", torch.float16, 2)):
+            ms_p = timeit(lambda: dag_posterior(a2, b2_, dt))
+            by_p = (8 + esz) * B * M * L
+            parts["dag_posterior_" + name] = {"ms": ms_p, "algorithmic_bytes": by_p, "gbs": by_p / ms_p / 1e6,
+                                              "frac": by_p / ms_p / 1e6 / peak_gbs, "torch_ops_ms": ms_t}
+        del a2, b2_
+
     if world > 1:
         dist.barrier()
     if rank == 0:

@@ -140,6 +140,13 @@ int dagb200_dag_best_alignment(const void *match, const void *links,
                                void *workspace, size_t workspace_bytes,
                                int32_t *status, void *stream);
 
+/* Next row of the path: the alignment posterior the S2S criterion derives from the two lattices,
+ * replacing five torch ops (criterions/s2s_dag_fastspeech2_loss.py:259-261 with custom_ops/dag_loss.py:303-311):
+ *   score[b][t][j] = exp(alpha + beta - logsumexp_j(alpha + beta)), 0 for rows without a finite cell (the reference's
+ *   NaN -> 0), written in out_dtype (DAGB200_F32 / F16 / BF16 = the feature dtype, :261).  alpha / beta fp32 [B][M][L]. */
+int dagb200_dag_posterior(const float *alpha, const float *beta, void *score, int out_dtype,
+                          int B, int M, int L, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,6 +335,36 @@ def test_device_prefetcher_overlapped_inputs_give_identical_results():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 40, 12, 39), (2, 1024, 40, 1023), (2, 301, 17, 64)])
+def test_dag_posterior_matches_the_criterion_formula(shape, dtype):
+    """daspeech_b200.posterior: the S2S criterion's posterior (s2s_dag_fastspeech2_loss.py:259-262) from the lattices of
+    dag_loss_with_alpha_beta, against the reference's own sequence of torch ops (with logsumexp_keepdim as exported)."""
+    from daspeech_b200.posterior import dag_posterior, dag_expected_features
+    B, L, M, T = shape
+    match, links, olen, tlen = oracle.make_lattice(B, L, M, T, seed=11 + L, ragged=True)
+    m, lk, ol, tl = cu(match), cu(links), cu(olen), cu(tlen)
+    m.requires_grad_()
+    _, (alpha, beta) = ops.dag_loss_with_alpha_beta(m, lk, ol, tl)
+    alpha[0, -1] = float("-inf")                      # a row without any finite cell: the reference's NaN -> 0
+    feats = torch.randn(B, L, 48, device=DEV).to(dtype).requires_grad_()
+    ref = (alpha + beta - ops.logsumexp_keepdim(alpha + beta, -1)).exp()
+    ref.masked_fill_(torch.isnan(ref), 0)
+    got = dag_posterior(alpha, beta, dtype)
+    assert got.dtype == dtype and got.shape == ref.shape
+    tol = {torch.float32: 2e-5, torch.float16: 1e-3, torch.bfloat16: 8e-3}[dtype]
+    assert torch.allclose(got.float(), ref.to(dtype).float(), rtol=tol, atol=tol * 1e-2)
+    assert torch.all(got[0, -1] == 0)
+    rows = got.float().sum(-1)
+    live = torch.isfinite(alpha + beta).any(-1)
+    assert torch.allclose(rows[live], torch.ones_like(rows[live]), atol=5 * tol)
+    z = dag_expected_features(alpha, beta, feats)
+    zr = torch.matmul(ref.to(feats), feats.detach())
+    assert torch.allclose(z.float(), zr.float(), rtol=10 * tol, atol=10 * tol)
+    z.float().sum().backward()
+    assert feats.grad is not None and torch.isfinite(feats.grad).all() and m.grad is None
+
+
 def test_logsoftmax_gather_layouts_and_errors():
     x = torch.randn(2, 5, 64, device=DEV)
     idx_full = torch.randint(0, 64, (2, 5, 3), device=DEV)   # genuinely strided (non-expanded) indices
