@@ -432,6 +432,18 @@ def main():
             parts["dag_posterior_" + name] = {"ms": ms_p, "algorithmic_bytes": by_p, "gbs": by_p / ms_p / 1e6,
                                               "frac": by_p / ms_p / 1e6 / peak_gbs, "torch_ops_ms": ms_t}
         del a2, b2_
+        # next row: GLAT force-emit masking, fused vs the criterion's torch expression
+        from daspeech_b200.glat import glat_force_emit
+        mm = torch.zeros(B, M, L, dtype=torch.bool, device=dev)
+        mm.scatter_(1, torch.randint(0, M, (B, 1, L), device=dev), True)
+        keepm = torch.rand(B, L, device=dev) < 0.3
+        prevm = keepm.unsqueeze(1)
+        ms_g = timeit(lambda: glat_force_emit(match, mm, keepm))
+        ms_gt = timeit(lambda: match.masked_fill(prevm, 0) + match.masked_fill(~mm, float("-inf")).masked_fill(~prevm, 0))
+        by_g = 9 * B * M * L
+        parts["glat_force_emit"] = {"ms": ms_g, "algorithmic_bytes": by_g, "gbs": by_g / ms_g / 1e6,
+                                    "frac": by_g / ms_g / 1e6 / peak_gbs, "torch_ops_ms": ms_gt}
+        del mm, keepm, prevm
 
     if world > 1:
         dist.barrier()

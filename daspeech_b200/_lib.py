@@ -39,6 +39,7 @@ SIGNATURES = {
     "dagb200_dag_loss_backward_ws": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
                                             _int, _int, _int, _int, _int, _int, _vp, _sz, _vp]),
     "dagb200_dag_posterior": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "dagb200_glat_force_emit": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "dagb200_dag_best_alignment": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int,
                                           _vp, _sz, _vp, _vp]),

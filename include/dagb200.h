@@ -147,6 +147,14 @@ int dagb200_dag_best_alignment(const void *match, const void *links,
 int dagb200_dag_posterior(const float *alpha, const float *beta, void *score, int out_dtype,
                           int B, int M, int L, void *stream);
 
+/* Next row: GLAT force-emit masking of the emission plane between logsoftmax_gather and dag_loss,
+ * replacing five torch ops (criterions/nat_dag_loss.py:130-132).  match / out fp32 [B][M][L]; matchmask bool [B][M][L]
+ * (1 = the cell the glancing alignment chose), keep_word_mask bool [B][L] (1 = glanced vertex).
+ *   backward == 0: out = glanced ? (matchmask ? match : -inf) : match
+ *   backward != 0: out = glanced ? 0 : match   (match = incoming gradient; matchmask may be NULL)                      */
+int dagb200_glat_force_emit(const float *match, const unsigned char *matchmask, const unsigned char *keep_word_mask,
+                            float *out, int B, int M, int L, int backward, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

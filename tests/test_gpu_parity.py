@@ -365,6 +365,32 @@ def test_dag_posterior_matches_the_criterion_formula(shape, dtype):
     assert feats.grad is not None and torch.isfinite(feats.grad).all() and m.grad is None
 
 
+@pytest.mark.parametrize("shape", [(3, 12, 40), (2, 64, 1024), (2, 7, 33)])
+def test_glat_force_emit_matches_the_criterion_expression(shape):
+    """daspeech_b200.glat: the force-emit masking of nat_dag_loss.py:130-132, values and gradient, against the
+    criterion's own torch expression."""
+    from daspeech_b200.glat import glat_force_emit
+    B, M, L = shape
+    torch.manual_seed(3)
+    base = torch.randn(B, M, L, device=DEV) - 5
+    base[0, 1, 2] = float("-inf")
+    matchmask = torch.zeros(B, M, L, dtype=torch.bool, device=DEV)
+    matchmask.scatter_(1, torch.randint(0, M, (B, 1, L), device=DEV), True)      # one aligned target per vertex
+    keep = torch.rand(B, L, device=DEV) < 0.4
+    w = torch.randn(B, M, L, device=DEV)
+
+    m_ref = base.clone().requires_grad_()
+    prev = keep.unsqueeze(1)
+    ref = m_ref.masked_fill(prev, 0) + m_ref.masked_fill(~matchmask, float("-inf")).masked_fill(~prev, 0).detach()
+    m_new = base.clone().requires_grad_()
+    got = glat_force_emit(m_new, matchmask, keep)
+    assert torch.equal(got, ref)
+    fin = torch.isfinite(ref)
+    (ref[fin] * w[fin]).sum().backward()
+    (got[fin] * w[fin]).sum().backward()
+    assert torch.equal(m_new.grad, m_ref.grad)
+
+
 def test_logsoftmax_gather_layouts_and_errors():
     x = torch.randn(2, 5, 64, device=DEV)
     idx_full = torch.randint(0, 64, (2, 5, 3), device=DEV)   # genuinely strided (non-expanded) indices
