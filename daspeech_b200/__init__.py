@@ -2,6 +2,10 @@
 
 Public surface = the operator surface of the reference plugin's `DASpeech/custom_ops` package
 (custom_ops/__init__.py:1): the same eight names, same argument meaning, same autograd contracts.
+
+Beyond that surface (the callers either side of the path; imported explicitly):
+`daspeech_b200.posterior` (alignment posterior of the S2S criterion), `daspeech_b200.glat` (GLAT force-emit masking of the
+NAT criterion), `daspeech_b200.prefetch` (host -> device input prefetch), `daspeech_b200.dist` (utterance sharding).
 """
 from .custom_ops import (  # noqa: F401
     dag_loss,
