@@ -408,6 +408,8 @@ def main():
             logits = (torch.randn(B, L, V, device=dev) * 2).to(dt)
             idx = torch.randint(4, V, (B, M), device=dev).unsqueeze(1).expand(-1, L, -1)
             gsel = torch.randn(B, M, L, device=dev).transpose(1, 2)
+            ms_am = timeit(lambda: logits.argmax(-1))                                   # what the GLAT pass does first
+            ms_fa = timeit(lambda: k.logsoftmax_gather(logits, idx, False, want_argmax=True))
             ms_f = timeit(lambda: k.logsoftmax_gather(logits, idx, True))
             by_f = 2 * esz * B * L * V + 4 * B * L * M + 8 * B * M
             ms_b = timeit(lambda: k.logsoftmax_gather_backward(logits, idx, gsel))
@@ -415,7 +417,9 @@ def main():
             parts["logsoftmax_gather_" + name] = {"fwd_ms": ms_f, "fwd_gbs": by_f / ms_f / 1e6,
                                                   "fwd_frac": by_f / ms_f / 1e6 / peak_gbs,
                                                   "bwd_ms": ms_b, "bwd_gbs": by_b / ms_b / 1e6,
-                                                  "bwd_frac": by_b / ms_b / 1e6 / peak_gbs}
+                                                  "bwd_frac": by_b / ms_b / 1e6 / peak_gbs,
+                                                  "glat_pass_gather_with_fused_argmax_ms": ms_fa,
+                                                  "torch_argmax_alone_ms": ms_am}
             del logits, idx, gsel
 
         # next row of the path: the S2S criterion's alignment posterior, fused vs the criterion's torch ops

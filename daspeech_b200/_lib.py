@@ -28,6 +28,8 @@ SIGNATURES = {
     "dagb200_get_profile": (_int, [_vp, _int]),
     "dagb200_logsoftmax_gather": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                          _int, _int, _int, _int, _int, _vp]),
+    "dagb200_logsoftmax_gather_argmax": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp,
+                                                _int, _int, _int, _int, _int, _vp]),
     "dagb200_logsoftmax_gather_backward": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                                   _int, _int, _int, _int, _vp]),
     "dagb200_dag_loss_workspace_bytes": (_sz, [_int, _int, _int, _int]),

@@ -81,6 +81,45 @@ template <bool IS_MAX> __device__ __forceinline__ float block_allreduce(float v,
   return r;
 }
 
+// block-wide arg-max over 256 threads: larger value wins, then the smaller index (first occurrence, as torch.argmax on
+// CUDA returns); `redv` / `redi` are 8 entries of shared memory each
+__device__ __forceinline__ void block_allreduce_argmax(float &v, int &i, float *redv, int *redi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { redv[w] = v; redi[w] = i; }
+  __syncthreads();
+  v = redv[l & 7];
+  i = redi[l & 7];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+// arg-max over the vocabulary for rows the TMA-staged kernel does not take (any V / alignment / dtype): one CTA per row
+template <typename T>
+__global__ void __launch_bounds__(kLsgThreads)
+lsg_argmax_kernel(const T *__restrict__ logits, int64_t *__restrict__ amax, int V) {
+  __shared__ float redv[8];
+  __shared__ int redi[8];
+  const T *x = logits + (int64_t)blockIdx.x * V;
+  float v = neg_inf_f();
+  int i = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += kLsgThreads) {
+    const float f = (float)x[c];
+    if (f > v || i == 0x7fffffff) { v = f; i = c; }
+  }
+  block_allreduce_argmax(v, i, redv, redi);
+  if (threadIdx.x == 0) amax[blockIdx.x] = i;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward, register-resident: NV 16-byte vectors per thread (V <= NV * 256 * kElems)
 template <typename T, int NV, bool GRAD>
@@ -169,10 +208,11 @@ __device__ __forceinline__ void lsg_load_row(void *dst, const void *src, uint32_
                ::"r"(lsg_smem_u32(dst)), "l"(src), "r"(bytes), "r"(lsg_smem_u32(bar)) : "memory");
 }
 
-template <typename T, int NV, bool GRAD>
+template <typename T, int NV, bool GRAD, bool AMAX>
 __global__ void __launch_bounds__(kLsgThreads)
 lsg_fwd_tma_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int64_t isb, int64_t isl, int64_t iss,
-                   float *__restrict__ out, int64_t osb, int64_t osl, int64_t oss, int L, int V, int S, int groups) {
+                   float *__restrict__ out, int64_t osb, int64_t osl, int64_t oss, int L, int V, int S, int groups,
+                   int64_t *__restrict__ amax) {
   using VT = VecTraits<T>;
   constexpr int E = VT::kElems;
   extern __shared__ __align__(128) unsigned char lsg_smem[];
@@ -182,6 +222,7 @@ lsg_fwd_tma_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int6
   int *idxs = reinterpret_cast<int *>(outb + (size_t)S * (kLsgGroup + 1));     // [S]
   float *red = reinterpret_cast<float *>(idxs + S);                            // [16]
   uint64_t *full = reinterpret_cast<uint64_t *>(red + 16);                     // [kLsgStages]
+  int *redi = reinterpret_cast<int *>(full + kLsgStages);                      // [8] (arg-max variant)
 
   const int b = blockIdx.x / groups, l0 = (blockIdx.x % groups) * kLsgGroup;
   const int nrows = min(kLsgGroup, L - l0);
@@ -228,6 +269,20 @@ lsg_fwd_tma_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int6
     // raw target logits from the staged row (outb doubles as their parking place)
     for (int s = threadIdx.x; s < S; s += kLsgThreads) outb[s * (kLsgGroup + 1) + r] = VT::to_float(xs[idxs[s]]);
     const float rmax = block_allreduce<true>(tmax, red);
+    if (AMAX) {
+      // first index holding the row maximum: the smallest one among my elements, then a warp-wide integer minimum;
+      // the 8 warp results meet after the barrier of the sum reduction below
+      int tidx = 0x7fffffff;
+#pragma unroll
+      for (int k = NV - 1; k >= 0; k--) {
+        const int c = k * kLsgThreads + threadIdx.x;
+#pragma unroll
+        for (int e = E - 1; e >= 0; e--)
+          if (c < nvec && v[k][e] == rmax) tidx = c * E + e;
+      }
+      tidx = __reduce_min_sync(0xffffffffu, tidx);
+      if ((threadIdx.x & 31) == 0) redi[threadIdx.x >> 5] = tidx;
+    }
     // every thread is past its reads of this stage: refill it with the row kLsgStages ahead
     if (threadIdx.x == 0 && r + kLsgStages < nrows) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -240,6 +295,12 @@ lsg_fwd_tma_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int6
 #pragma unroll
       for (int e = 0; e < E; e++) { v[k][e] = __expf(v[k][e] - moff); tsum += v[k][e]; }
     const float rsum = block_allreduce<false>(tsum, red + 8);
+    if (AMAX && threadIdx.x == 0) {
+      int best = redi[0];
+#pragma unroll
+      for (int w = 1; w < kLsgThreads / 32; w++) best = min(best, redi[w]);
+      amax[(int64_t)b * L + l0 + r] = best;
+    }
     const float lsum = __logf(rsum);
     for (int s = threadIdx.x; s < S; s += kLsgThreads) {
       float *o = outb + s * (kLsgGroup + 1) + r;
@@ -283,23 +344,25 @@ lsg_fwd_tma_kernel(T *__restrict__ logits, const int64_t *__restrict__ idx, int6
 }
 
 static size_t lsg_fwd_tma_smem(size_t rowbytes, int S) {
-  return (size_t)kLsgStages * rowbytes + (size_t)S * (kLsgGroup + 1) * 4 + (size_t)S * 4 + 16 * 4 + kLsgStages * 8 + 16;
+  return (size_t)kLsgStages * rowbytes + (size_t)S * (kLsgGroup + 1) * 4 + (size_t)S * 4 + 16 * 4 + kLsgStages * 8 + 8 * 4 + 16;
 }
 
 template <typename T, int NV>
 static int launch_fwd_tma(T *logits, const int64_t *idx, int64_t isb, int64_t isl, int64_t iss, float *out,
                           int64_t osb, int64_t osl, int64_t oss, int B, int L, int V, int S, bool grad,
-                          cudaStream_t st) {
+                          cudaStream_t st, int64_t *amax) {
   const size_t smem = lsg_fwd_tma_smem((size_t)V * sizeof(T), S);
   const int groups = (L + kLsgGroup - 1) / kLsgGroup;
   const unsigned grid = (unsigned)((int64_t)B * groups);
-  if (grad) {
-    cudaFuncSetAttribute(lsg_fwd_tma_kernel<T, NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    lsg_fwd_tma_kernel<T, NV, true><<<grid, kLsgThreads, smem, st>>>(logits, idx, isb, isl, iss, out, osb, osl, oss, L, V, S, groups);
-  } else {
-    cudaFuncSetAttribute(lsg_fwd_tma_kernel<T, NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    lsg_fwd_tma_kernel<T, NV, false><<<grid, kLsgThreads, smem, st>>>(logits, idx, isb, isl, iss, out, osb, osl, oss, L, V, S, groups);
-  }
+#define DAGB200_LSG_LAUNCH(G, A)                                                                                      \
+  do {                                                                                                                \
+    cudaFuncSetAttribute(lsg_fwd_tma_kernel<T, NV, G, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+    lsg_fwd_tma_kernel<T, NV, G, A><<<grid, kLsgThreads, smem, st>>>(logits, idx, isb, isl, iss, out, osb, osl, oss,  \
+                                                                     L, V, S, groups, amax);                          \
+  } while (0)
+  if (grad) { if (amax) DAGB200_LSG_LAUNCH(true, true); else DAGB200_LSG_LAUNCH(true, false); }
+  else { if (amax) DAGB200_LSG_LAUNCH(false, true); else DAGB200_LSG_LAUNCH(false, false); }
+#undef DAGB200_LSG_LAUNCH
   DAGB200_CHECK_LAUNCH("lsg_fwd_tma_kernel");
   return 0;
 }
@@ -736,7 +799,7 @@ static int launch_fwd_reg(T *logits, const int64_t *idx, int64_t isb, int64_t is
 template <typename T>
 static int lsg_fwd_dispatch16(T *logits, const int64_t *idx, int64_t isb, int64_t isl, int64_t iss, float *out,
                               int64_t osb, int64_t osl, int64_t oss, int B, int L, int V, int S, bool grad,
-                              cudaStream_t st) {
+                              cudaStream_t st, int64_t *amax = nullptr) {
   constexpr int E = VecTraits<T>::kElems;
   const bool aligned = (V % E == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   const int nvec = V / E;
@@ -744,10 +807,14 @@ static int lsg_fwd_dispatch16(T *logits, const int64_t *idx, int64_t isb, int64_
   // TMA-staged path: rows of <= 32 KB that keep at least two CTAs per SM resident
   static const bool no_tma = getenv("DAGB200_LSG_NOTMA") != nullptr;
   if (!no_tma && aligned && need <= 8 && (size_t)V * sizeof(T) <= 32768 && lsg_fwd_tma_smem((size_t)V * sizeof(T), S) <= 110 * 1024) {
-    if (need <= 1) return launch_fwd_tma<T, 1>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
-    if (need <= 2) return launch_fwd_tma<T, 2>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
-    if (need <= 4) return launch_fwd_tma<T, 4>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
-    return launch_fwd_tma<T, 8>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
+    if (need <= 1) return launch_fwd_tma<T, 1>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st, amax);
+    if (need <= 2) return launch_fwd_tma<T, 2>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st, amax);
+    if (need <= 4) return launch_fwd_tma<T, 4>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st, amax);
+    return launch_fwd_tma<T, 8>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st, amax);
+  }
+  if (amax) {   // not a TMA-staged shape: the arg-max runs as its own pass BEFORE the row may be overwritten
+    lsg_argmax_kernel<T><<<(unsigned)((int64_t)B * L), kLsgThreads, 0, st>>>(logits, amax, V);
+    DAGB200_CHECK_LAUNCH("lsg_argmax_kernel");
   }
   if (aligned && need <= 16 && S <= 8192) {
     if (need <= 1) return launch_fwd_reg<T, 1>(logits, idx, isb, isl, iss, out, osb, osl, oss, B, L, V, S, grad, st);
@@ -836,6 +903,30 @@ extern "C" int dagb200_logsoftmax_gather(void *logits, int dtype, const int64_t 
     }
     default:
       set_error("logsoftmax_gather: unsupported dtype %d", dtype);
+      return DAGB200_EDTYPE;
+  }
+}
+
+extern "C" int dagb200_logsoftmax_gather_argmax(void *logits, int dtype, const int64_t *idx, int64_t isb, int64_t isl,
+                                                int64_t iss, void *out, int64_t osb, int64_t osl, int64_t oss,
+                                                int64_t *argmax, int B, int L, int V, int S, int require_gradient,
+                                                void *stream) {
+  DAGB200_CHECK_ARG(B >= 0 && L >= 0 && V >= 1 && S >= 0, DAGB200_EINVAL,
+                    "logsoftmax_gather_argmax: bad sizes B=%d L=%d V=%d S=%d", B, L, V, S);
+  if ((int64_t)B * L == 0) return 0;
+  DAGB200_CHECK_ARG(logits && out && argmax && (idx || S == 0), DAGB200_EINVAL, "logsoftmax_gather_argmax: null pointer");
+  DAGB200_CHECK_ARG((int64_t)B * L < (1ll << 31), DAGB200_ELIMIT, "logsoftmax_gather_argmax: B*L too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool grad = require_gradient != 0;
+  switch (dtype) {
+    case DAGB200_F32:
+      return lsg_fwd_dispatch16<float>((float *)logits, idx, isb, isl, iss, (float *)out, osb, osl, oss, B, L, V, S, grad, st, argmax);
+    case DAGB200_F16:
+      return lsg_fwd_dispatch16<__half>((__half *)logits, idx, isb, isl, iss, (float *)out, osb, osl, oss, B, L, V, S, grad, st, argmax);
+    case DAGB200_BF16:
+      return lsg_fwd_dispatch16<__nv_bfloat16>((__nv_bfloat16 *)logits, idx, isb, isl, iss, (float *)out, osb, osl, oss, B, L, V, S, grad, st, argmax);
+    default:
+      set_error("logsoftmax_gather_argmax: unsupported dtype %d (fp32 / fp16 / bf16)", dtype);
       return DAGB200_EDTYPE;
   }
 }

@@ -184,7 +184,7 @@ class _DagKernel:
         _check_status(status)
         return alpha, path
 
-    def logsoftmax_gather(self, word_ins_out, select_idx, require_gradient) -> Tensor:
+    def logsoftmax_gather(self, word_ins_out, select_idx, require_gradient, want_argmax=False):
         _check(word_ins_out.is_cuda, "word_ins_out must be a CUDA tensor")
         _check(select_idx.is_cuda, "select_idx must be a CUDA tensor")
         _check(word_ins_out.dim() == 3, "word_ins_out dim != 3")
@@ -205,13 +205,26 @@ class _DagKernel:
             result = torch.empty((bsz, prelen, slen), dtype=out_dtype, device=word_ins_out.device)
         isb, isl, iss = select_idx.stride()
         osb, osl, oss = result.stride()
+        if want_argmax:
+            # fused with the gather (one pass over the logits instead of two); fp64 has no fused variant
+            if word_ins_out.dtype == torch.float64:
+                amax = word_ins_out.argmax(-1)
+            else:
+                amax = torch.empty((bsz, prelen), dtype=torch.long, device=word_ins_out.device)
+                with torch.cuda.device(word_ins_out.device):
+                    rc = self.lib.dagb200_logsoftmax_gather_argmax(
+                        _ptr(word_ins_out), _DTYPE_CODE[word_ins_out.dtype], _ptr(select_idx), isb, isl, iss,
+                        _ptr(result), osb, osl, oss, _ptr(amax), bsz, prelen, vocabsize, slen,
+                        int(bool(require_gradient)), _stream())
+                _lib.check(rc, "logsoftmax_gather_argmax")
+                return result, amax
         with torch.cuda.device(word_ins_out.device):
             rc = self.lib.dagb200_logsoftmax_gather(_ptr(word_ins_out), _DTYPE_CODE[word_ins_out.dtype],
                                                     _ptr(select_idx), isb, isl, iss, _ptr(result), osb, osl, oss,
                                                     bsz, prelen, vocabsize, slen, int(bool(require_gradient)),
                                                     _stream())
         _lib.check(rc, "logsoftmax_gather")
-        return result
+        return (result, amax) if want_argmax else result
 
     # fused replacement of the two torch ops in DagLogsoftmaxGatherFunc.backward (dag_loss.py:294-295)
     def logsoftmax_gather_backward(self, probs_inout, select_idx, grad_output) -> Tensor:
@@ -369,6 +382,31 @@ class DagLogsoftmaxGatherFunc(Function):
 
 
 dag_logsoftmax_gather_inplace = DagLogsoftmaxGatherFunc.apply
+
+
+class DagLogsoftmaxGatherArgmaxFunc(Function):
+    r"""`dag_logsoftmax_gather_inplace` that also returns `word_ins_out.argmax(-1)` of the RAW logits, computed in the
+    same pass (the GLAT pass of the criterion takes the arg-max right before the gather, nat_dag_loss.py:209-213).
+    Returns (word_ins_out, selected_result, pred_tokens); pred_tokens is long [B, L] and not differentiable."""
+
+    @staticmethod
+    def forward(ctx, word_ins_out, select_idx):
+        require_gradient = ctx.needs_input_grad[0]
+        selected_result, pred = get_dag_kernel().logsoftmax_gather(word_ins_out, select_idx, require_gradient, want_argmax=True)
+        ctx.mark_dirty(word_ins_out)
+        ctx.mark_non_differentiable(pred)
+        ctx.set_materialize_grads(False)
+        if require_gradient:
+            ctx.save_for_backward(word_ins_out, select_idx)
+            ctx.has_backward = False
+        return word_ins_out, selected_result, pred
+
+    @staticmethod
+    def backward(ctx, grad_word_ins_out, grad_output, grad_pred):
+        return DagLogsoftmaxGatherFunc.backward(ctx, grad_word_ins_out, grad_output)
+
+
+dag_logsoftmax_gather_argmax_inplace = DagLogsoftmaxGatherArgmaxFunc.apply
 
 
 # =====================================================================================================

@@ -140,6 +140,14 @@ int dagb200_dag_best_alignment(const void *match, const void *links,
                                void *workspace, size_t workspace_bytes,
                                int32_t *status, void *stream);
 
+/* GLAT pass: dagb200_logsoftmax_gather plus the arg-max over the vocabulary of every row (int64 [B][L], first index of
+ * the maximum), which the criterion computes with a separate pass over the logits right before the gather
+ * (criterions/nat_dag_loss.py:209 `pred_tokens = word_ins_out.argmax(-1)`, then :213).  Same arguments otherwise;
+ * fp32 / fp16 / bf16 logits.                                                                                        */
+int dagb200_logsoftmax_gather_argmax(void *logits, int dtype, const int64_t *select_idx, int64_t isb, int64_t isl,
+                                     int64_t iss, void *out, int64_t osb, int64_t osl, int64_t oss,
+                                     int64_t *argmax, int B, int L, int V, int S, int require_gradient, void *stream);
+
 /* Next row of the path: the alignment posterior the S2S criterion derives from the two lattices,
  * replacing five torch ops (criterions/s2s_dag_fastspeech2_loss.py:259-261 with custom_ops/dag_loss.py:303-311):
  *   score[b][t][j] = exp(alpha + beta - logsumexp_j(alpha + beta)), 0 for rows without a finite cell (the reference's

@@ -391,6 +391,40 @@ def test_glat_force_emit_matches_the_criterion_expression(shape):
     assert torch.equal(m_new.grad, m_ref.grad)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("VS", [(512, 32), (4104, 40), (1001, 7)])
+def test_logsoftmax_gather_with_fused_argmax(dtype, VS):
+    """dag_logsoftmax_gather_argmax_inplace: the gather plus `word_ins_out.argmax(-1)` of the raw logits in one pass
+    (nat_dag_loss.py:209-213); TMA-staged shapes and the generic arg-max kernel; ties resolve to the first index."""
+    torch.manual_seed(9)
+    V, S = VS
+    B, L = 2, 19
+    x0 = (torch.randn(B, L, V, device=DEV) * 2).to(dtype)
+    x0[0, 0, 5] = x0[0, 0].max() + 1            # an exact tie: both indices hold the row maximum
+    x0[0, 0, 77] = x0[0, 0, 5]
+    idx = torch.randint(0, V, (B, S), device=DEV).unsqueeze(1).expand(-1, L, -1)
+    want_pred = x0.argmax(-1)
+    want_pred[0, 0] = 5
+    ref = torch.log_softmax(x0.double(), -1).gather(-1, idx)
+    leaf = x0.clone().requires_grad_()
+    out, sel, pred = ops.dag_logsoftmax_gather_argmax_inplace(leaf * 1, idx)
+    assert pred.dtype == torch.long and not pred.requires_grad
+    assert torch.equal(pred, want_pred)
+    tol = 1e-10 if dtype == torch.float64 else 2e-5
+    assert torch.allclose(sel.double(), ref, rtol=tol, atol=10 * tol)
+    w = torch.randn_like(sel)
+    g1 = torch.autograd.grad((sel * w).sum(), [leaf])[0]
+    leaf2 = x0.clone().requires_grad_()
+    _, sel2 = ops.dag_logsoftmax_gather_inplace(leaf2 * 1, idx)
+    g2 = torch.autograd.grad((sel2 * w).sum(), [leaf2])[0]
+    # duplicate targets are scattered with shared-memory atomics: equal up to the order of the additions
+    assert relerr(g1.double().cpu().numpy(), g2.double().cpu().numpy()) <= (1e-5 if dtype in (torch.float32, torch.float64) else 2e-2)
+    with torch.no_grad():
+        x1 = x0.clone()
+        _, _, pred2 = ops.dag_logsoftmax_gather_argmax_inplace(x1, idx)
+    assert torch.equal(x1, x0) and torch.equal(pred2, want_pred)
+
+
 def test_logsoftmax_gather_layouts_and_errors():
     x = torch.randn(2, 5, 64, device=DEV)
     idx_full = torch.randint(0, 64, (2, 5, 3), device=DEV)   # genuinely strided (non-expanded) indices
