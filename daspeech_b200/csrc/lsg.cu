@@ -32,6 +32,10 @@ template <> struct VecTraits<float> {
   }
   __device__ static __forceinline__ float to_float(float v) { return v; }
   __device__ static __forceinline__ float from_float(float v) { return v; }
+  __device__ static __forceinline__ uint4 scale(const uint4 &u, float sc) {
+    return make_uint4(__float_as_uint(__uint_as_float(u.x) * sc), __float_as_uint(__uint_as_float(u.y) * sc),
+                      __float_as_uint(__uint_as_float(u.z) * sc), __float_as_uint(__uint_as_float(u.w) * sc));
+  }
 };
 template <> struct VecTraits<__half> {
   static constexpr int kElems = 8;
@@ -48,6 +52,16 @@ template <> struct VecTraits<__half> {
   }
   __device__ static __forceinline__ float to_float(__half v) { return __half2float(v); }
   __device__ static __forceinline__ __half from_float(float v) { return __float2half_rn(v); }
+  // element-wise product with a scalar IN the 16-bit type (one rounding per element, as a torch half multiply)
+  __device__ static __forceinline__ uint4 scale(const uint4 &u, float sc) {
+    const __half2 s2 = __float2half2_rn(sc);
+    uint4 r;
+    const __half2 *a = reinterpret_cast<const __half2 *>(&u);
+    __half2 *o = reinterpret_cast<__half2 *>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = __hmul2(a[i], s2);
+    return r;
+  }
 };
 template <> struct VecTraits<__nv_bfloat16> {
   static constexpr int kElems = 8;
@@ -64,6 +78,15 @@ template <> struct VecTraits<__nv_bfloat16> {
   }
   __device__ static __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
   __device__ static __forceinline__ __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+  __device__ static __forceinline__ uint4 scale(const uint4 &u, float sc) {
+    const __nv_bfloat162 s2 = __float2bfloat162_rn(sc);
+    uint4 r;
+    const __nv_bfloat162 *a = reinterpret_cast<const __nv_bfloat162 *>(&u);
+    __nv_bfloat162 *o = reinterpret_cast<__nv_bfloat162 *>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = __hmul2(a[i], s2);
+    return r;
+  }
 };
 
 // block-wide all-reduce over 256 threads (8 warps); `red` is 8 floats of shared memory per use
@@ -720,14 +743,11 @@ lsg_bwd_tma16_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int
     const T *xs = reinterpret_cast<const T *>(stages + (size_t)st * rowbytes);
     const float neg = red[8 * kLsgGroup + r];
     lsg_mbar_wait(full + st, (r / STAGES) & 1);
-    float f[NV][E];
+    uint4 u[NV];
 #pragma unroll
     for (int k = 0; k < NV; k++) {
       const int c = k * kLsgThreads + threadIdx.x;
-      if (c < nvec) {
-        const uint4 u = reinterpret_cast<const uint4 *>(xs)[c];
-        VT::unpack(u, f[k]);
-      }
+      if (c < nvec) u[k] = reinterpret_cast<const uint4 *>(xs)[c];
     }
     __syncthreads();
     if (threadIdx.x == 0 && r + STAGES < nrows) {   // every thread is past its reads of this stage
@@ -739,16 +759,23 @@ lsg_bwd_tma16_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int
     for (int k = 0; k < NV; k++) {
       const int c = k * kLsgThreads + threadIdx.x;
       if (c < nvec) {
+        // probs * (-sum) in the row's dtype: one packed multiply per pair, rounded once like the reference's multiply
+        // (dag_loss.py:294); only the few vectors that hold a target leave the packed form for the scatter
+        uint4 o = VT::scale(u[k], neg);
+        const int q0 = boff[c], q1 = boff[c + 1];
+        if (q1 > q0) {
+          float f[E];
+          VT::unpack(o, f);
+          for (int q = q0; q < q1; q++) {
+            const int s = blist[q];
+            const int col = idxs[s] - c * E;
+            const float gv = gbuf[s * (kLsgGroup + 1) + r];
 #pragma unroll
-        for (int e = 0; e < E; e++) f[k][e] = VT::to_float(VT::from_float(f[k][e] * neg));
-        for (int q = boff[c]; q < boff[c + 1]; q++) {
-          const int s = blist[q];
-          const int col = idxs[s] - c * E;
-          const float gv = gbuf[s * (kLsgGroup + 1) + r];
-#pragma unroll
-          for (int e = 0; e < E; e++) f[k][e] += (e == col) ? gv : 0.f;
+            for (int e = 0; e < E; e++) f[e] += (e == col) ? gv : 0.f;
+          }
+          o = VT::pack(f);
         }
-        reinterpret_cast<uint4 *>(x)[c] = VT::pack(f[k]);
+        reinterpret_cast<uint4 *>(x)[c] = o;
       }
     }
   }
