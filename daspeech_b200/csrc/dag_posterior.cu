@@ -59,10 +59,16 @@ dag_posterior_vec_kernel(const float *__restrict__ alpha, const float *__restric
   mx = post_block_reduce(mx, true, red);
   const bool empty = !(mx > neg_inf_f());       // a row without any finite cell: the reference's NaN -> 0
   float sum = 0.f;
+  const float mo2 = (empty ? 0.f : mx) * kLog2e;        // exp(x - m) = 2^(x log2e - m log2e): one FFMA + one MUFU.EX2
 #pragma unroll
   for (int k = 0; k < NV; k++)
 #pragma unroll
-    for (int e = 0; e < 4; e++) { x[k][e] = empty ? 0.f : __expf(x[k][e] - mx); sum += x[k][e]; }
+    for (int e = 0; e < 4; e++) {
+      float pz;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pz) : "f"(fmaf(x[k][e], kLog2e, -mo2)));
+      x[k][e] = empty ? 0.f : pz;
+      sum += x[k][e];
+    }
   sum = post_block_reduce(sum, false, red + 8);
   const float inv = empty ? 0.f : __fdividef(1.f, sum);
   OutT *o = score + row * L;
