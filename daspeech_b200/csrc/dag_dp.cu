@@ -370,26 +370,18 @@ static int check_dp_args(const char *who, const void *match, const void *links, 
 using namespace dagb200;
 
 namespace dagb200 {
-size_t dp2_workspace_bytes(int B, int M, int L);
-bool dp2_supported(int M, int L);
 extern int g_exact_mode;
-bool dp3_supported(int M, int L);
 bool dp4_supported(int M, int L);
+size_t dp4_workspace_bytes(int B, int M, int L);
 int launch_alpha_beta_tcgen05(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
-                              float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
-                              int32_t *status, cudaStream_t st);
-int launch_alpha_beta_colmajor(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
-                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
-                               int32_t *status, cudaStream_t st);
-int launch_alpha_beta_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
                               float *alpha, float *beta, int B, int M, int L, int Tl, bool grad, void *workspace,
                               int32_t *status, cudaStream_t st);
 }  // namespace dagb200
 
 extern "C" size_t dagb200_dag_loss_workspace_bytes(int B, int M, int L, int T) {
   (void)T;
-  if (B <= 0 || M < 1 || L < 1 || !dp2_supported(M, L)) return 0;
-  return dp2_workspace_bytes(B, M, L);
+  if (B <= 0 || M < 1 || L < 1 || !dp4_supported(M, L)) return 0;
+  return dp4_workspace_bytes(B, M, L);
 }
 
 extern "C" int dagb200_dag_loss(const void *match, const void *links, const int64_t *output_length,
@@ -409,17 +401,12 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
     cudaError_t e = cudaMemsetAsync(beta, 0, (size_t)B * M * L * esz, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(beta)");
   }
-  static const int dp_version = getenv("DAGB200_DP") ? atoi(getenv("DAGB200_DP")) : 4;
-  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp_version >= 4 && dp4_supported(M, L) &&
-      workspace_bytes >= dp2_workspace_bytes(B, M, L))
+  // fp32 with a workspace: blocked recurrences, far sums on tcgen05 (dag_dp4.cu).  Everything else -- fp64, exact
+  // mode, no workspace, lattices beyond the shared memory of the blocked kernel (L > ~1760) -- runs the exact
+  // log-domain kernels below.
+  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp4_supported(M, L) &&
+      workspace_bytes >= dp4_workspace_bytes(B, M, L))
     return launch_alpha_beta_tcgen05((const float *)match, (const float *)links, output_length, target_length,
-                                     (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
-  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp_version >= 3 && dp3_supported(M, L) &&
-      workspace_bytes >= dp2_workspace_bytes(B, M, L))
-    return launch_alpha_beta_colmajor((const float *)match, (const float *)links, output_length, target_length,
-                                      (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
-  if (dtype == DAGB200_F32 && !g_exact_mode && workspace && dp2_supported(M, L) && workspace_bytes >= dp2_workspace_bytes(B, M, L))
-    return launch_alpha_beta_blocked((const float *)match, (const float *)links, output_length, target_length,
                                      (float *)alpha, (float *)beta, B, M, L, T, grad, workspace, status, st);
   if (dtype == DAGB200_F32)
     return launch_alpha_beta<float>((const float *)match, (const float *)links, output_length, target_length,

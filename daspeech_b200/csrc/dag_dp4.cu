@@ -1,7 +1,8 @@
 // dag_dp4.cu -- column-major blocked alpha / beta recurrences with the far-predecessor GEMM on tcgen05 (sm_100a).
 //
-// Same organisation as dag_dp3.cu (see there: passes of 8 chunks, 8 chain warps running the fp64 diagonal blocks one
-// column apart, two phases per vertex block), but the far predecessor sums run on the 5th-generation tensor cores:
+// Vertices in blocks of 32 swept in order, target rows in chunks of 32, a pass = 8 chunks = 256 rows; 8 chain warps run
+// the fp64 diagonal blocks of the 8 chunks one column apart (lanes = rows, push formulation), two phases per vertex
+// block; the far predecessor sums run on the 5th-generation tensor cores:
 //
 //   D[128 rows x 32 destination vertices] (TMEM, fp32) = A[128 x 32] (smem, bf16, K-major) * B[32 x 32]^T (smem, bf16)
 //   tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 32, K = 16, canonical no-swizzle core-matrix layout (8 rows x 16
@@ -15,8 +16,8 @@
 //     8 epilogue warps (thread = row) read it back with tcgen05.ld.32x32b, scale it by the exact power of two
 //     2^(frame of the source row - running frame) and add it to the row's far sums in registers (online maximum), then
 //     hand the sums to the chain warps through shared memory.
-//   The per-(row, source block) rescale that kept dp3 on mma.sync (rescaling the A fragments in registers) moves to
-//   the accumulator side, which is what makes the tcgen05 form possible.
+//   The per-(row, source block) power-of-two rescale lives on the accumulator side, which is what makes the tcgen05
+//   form possible (the A operand is never rewritten per use).
 #include <cstdio>
 #include <cstdlib>
 
@@ -48,12 +49,6 @@ __device__ int g_evq = 27;
 __device__ long long g_ep[2][32][4];
 __device__ int g_evbase[4];
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 // 2^d as float for d <= 127; exactly 0 below the normal range
 __device__ __forceinline__ float pow2i(int d) { return __int_as_float((max(d, -127) + 127) << 23); }
 // 2^d as double, exactly 0 for d <= -1023, clamped above
@@ -121,18 +116,6 @@ __device__ __forceinline__ void st_relaxed_u64(void *p, unsigned long long v) {
 }
 __device__ __forceinline__ void st_release_s32(int *p, int v) {
   asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-
-// one element of a fragment tile of the A operand (see dag_tiles.cuh / dag_dp2.cu)
-__device__ __forceinline__ void write_frag_elem(uint4 *tile, int row, int k, float v) {
-  const int slice = row >> 4, r16 = row & 15, ks = k >> 4, k16 = k & 15;
-  const int gid = r16 & 7, reg = (r16 >> 3) | ((k16 >> 3) << 1), tig = (k16 & 7) >> 1, half = k16 & 1;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-  __nv_bfloat16 *ph = reinterpret_cast<__nv_bfloat16 *>(tile + (slice * 4 + ks * 2 + 0) * 32 + gid * 4 + tig);
-  __nv_bfloat16 *pl = reinterpret_cast<__nv_bfloat16 *>(tile + (slice * 4 + ks * 2 + 1) * 32 + gid * 4 + tig);
-  ph[reg * 2 + half] = h;
-  pl[reg * 2 + half] = l;
 }
 
 // ---- tcgen05 / TMEM helpers (encodings verified stand-alone in tools/tcgen05_probe.cu) ----------------------
@@ -1114,7 +1097,9 @@ dag_alpha_beta_tcgen05_kernel(const float *__restrict__ match, const int64_t *__
                               int32_t *__restrict__ status, float l2frac) {
   alpha_beta_body<false>(match, olen, tlen, alpha, beta, ws, M, L, Tl, lay, status, 0, l2frac);
 }
-// the same kernel with the in-kernel timers / timelines compiled in (DAGB200_DP4_DEBUG != 0)
+#ifdef DAGB200_DEBUG_KERNELS
+// the same kernel with the in-kernel timers / timelines compiled in (build with -DDAGB200_DEBUG_KERNELS, run with
+// DAGB200_DP4_DEBUG != 0); not part of the product library
 __global__ void __launch_bounds__(kThreads, 1)
 dag_alpha_beta_tcgen05_debug_kernel(const float *__restrict__ match, const int64_t *__restrict__ olen,
                                     const int64_t *__restrict__ tlen, float *__restrict__ alpha, float *__restrict__ beta,
@@ -1122,6 +1107,7 @@ dag_alpha_beta_tcgen05_debug_kernel(const float *__restrict__ match, const int64
                                     int32_t *__restrict__ status, int dbg, float l2frac) {
   alpha_beta_body<true>(match, olen, tlen, alpha, beta, ws, M, L, Tl, lay, status, dbg, l2frac);
 }
+#endif
 
 }  // namespace dp4
 
@@ -1134,7 +1120,9 @@ size_t dp4_smem_bytes(int M, int L) {
 
 bool dp4_supported(int M, int L) { return L >= 1 && M >= 2 && dp4_smem_bytes(M, L) <= 227 * 1024; }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, int fmt,
+size_t dp4_workspace_bytes(int B, int M, int L) { return TileLayout::make(L, M).sample_bytes * (size_t)B; }
+
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl,
                     cudaStream_t st);
 
 int launch_alpha_beta_tcgen05(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
@@ -1142,26 +1130,30 @@ int launch_alpha_beta_tcgen05(const float *match, const float *links, const int6
                               int32_t *status, cudaStream_t st) {
   using namespace dp4;
   prof_mark(0, st);
-  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, 1, st);
+  int rc = launch_dag_prep(links, olen, workspace, B, M, L, Tl, st);
   if (rc) return rc;
   prof_mark(1, st);
   TileLayout lay = TileLayout::make(L, M);
   dim3 grid(B, grad ? 2 : 1);
   const size_t smem = dp4_smem_bytes(M, L);
-  static const int dbg = getenv("DAGB200_DP4_DEBUG") ? atoi(getenv("DAGB200_DP4_DEBUG")) : 0;
   // number of leading source blocks whose A slabs are requested evict_last (about 50 MB pinned at B = 64; measured at C2:
   // DRAM reads 1.64 -> 1.09 GB, L2 hit rate 27 -> 42 %, 631 -> 607 us); DAGB200_DP4_L2FRAC=0 switches the hints off
   static const float l2env = getenv("DAGB200_DP4_L2FRAC") ? (float)atof(getenv("DAGB200_DP4_L2FRAC")) : -1.f;
   const float l2frac = l2env >= 0.f ? l2env : (float)(B <= 64 ? 12 : (768 / B > 2 ? 768 / B : 2));
+#ifdef DAGB200_DEBUG_KERNELS
+  static const int dbg = getenv("DAGB200_DP4_DEBUG") ? atoi(getenv("DAGB200_DP4_DEBUG")) : 0;
   if (dbg) {
     cudaFuncSetAttribute(dag_alpha_beta_tcgen05_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dag_alpha_beta_tcgen05_debug_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
                                                                       M, L, Tl, lay, status, dbg, l2frac);
-  } else {
-    cudaFuncSetAttribute(dag_alpha_beta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dag_alpha_beta_tcgen05_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
-                                                                M, L, Tl, lay, status, l2frac);
+    DAGB200_CHECK_LAUNCH("dag_alpha_beta_tcgen05_debug_kernel");
+    prof_mark(2, st);
+    return 0;
   }
+#endif
+  cudaFuncSetAttribute(dag_alpha_beta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dag_alpha_beta_tcgen05_kernel<<<grid, kThreads, smem, st>>>(match, olen, tlen, alpha, beta, (unsigned char *)workspace,
+                                                              M, L, Tl, lay, status, l2frac);
   DAGB200_CHECK_LAUNCH("dag_alpha_beta_tcgen05_kernel");
   prof_mark(2, st);
   return 0;

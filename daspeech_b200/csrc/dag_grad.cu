@@ -113,9 +113,6 @@ grad_links_kernel(const T *__restrict__ go, const T *__restrict__ alpha, const T
 }  // namespace dagb200
 
 namespace dagb200 {
-int launch_grad_links_mma(const float *go, const float *alpha, const float *beta, const float *links,
-                          const int64_t *olen, const int64_t *tlen, float *gl, int B, int M, int L, int Tl,
-                          cudaStream_t st);
 int g_exact_mode = 0;
 }  // namespace dagb200
 
@@ -192,11 +189,7 @@ extern "C" int dagb200_dag_loss_backward(const void *grad_output, const void *al
                                                       (const float *)match, (float *)grad_match, lat, total);
     DAGB200_CHECK_LAUNCH("grad_match_kernel");
     prof_mark(4, st);
-    if (!g_exact_mode) {
-      int rc = launch_grad_links_mma((const float *)grad_output, (const float *)alpha, (const float *)beta,
-                                     (const float *)links, output_length, target_length, (float *)grad_links, B, M, L, T, st);
-      if (rc) return rc;
-    } else {
+    {
       const size_t smem = (size_t)M * kGlRows * sizeof(float);
       DAGB200_CHECK_ARG(smem <= 200 * 1024, DAGB200_ELIMIT, "dag_loss_backward: M=%d too large", M);
       if (smem > 48 * 1024) cudaFuncSetAttribute(grad_links_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -13,15 +13,6 @@ __device__ __forceinline__ uint32_t pack_bf16_pair(float lo_elem, float hi_elem)
 }
 __device__ __forceinline__ float bf16_hi_part(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// reg(nt, r) of the fragment order, from an operand tile addressed Bop(k, n)
-template <bool LO, typename F>
-__device__ __forceinline__ uint32_t frag_reg(F bop, int ks, int nt, int r, int gid, int tig) {
-  const int k = 16 * ks + 2 * tig + 8 * r, n = 8 * nt + gid;
-  float x0 = bop(k, n), x1 = bop(k + 1, n);
-  if (LO) { x0 -= bf16_hi_part(x0); x1 -= bf16_hi_part(x1); }
-  return pack_bf16_pair(x0, x1);
-}
-
 // pass 1: per-source-vertex maximum over the valid successors (one warp per vertex, coalesced along k)
 __global__ void __launch_bounds__(256)
 dag_rowmax_kernel(const float *__restrict__ links, const int64_t *__restrict__ olen, unsigned char *__restrict__ ws,
@@ -51,7 +42,7 @@ dag_rowmax_kernel(const float *__restrict__ links, const int64_t *__restrict__ o
 // pass 2: one CTA (4 warps) per 32x32 tile (I <= J): P' = exp(links - rmax) into the operand layouts
 __global__ void __launch_bounds__(128)
 dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ olen, unsigned char *__restrict__ ws,
-                 int L, int Tl, TileLayout lay, int fmt) {
+                 int L, int Tl, TileLayout lay) {
   __shared__ float tile[kBlk][kBlk + 1];
   const int I = blockIdx.y, b = blockIdx.z;
   const int J = I + blockIdx.x;                    // blockIdx.x = block distance, 0 .. band
@@ -79,21 +70,15 @@ dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ ol
     tile[ii][lane] = __expf(v[r] - (rm == neg_inf_f() ? 0.f : rm));   // exp(-inf) = 0
   }
   __syncthreads();
-  const int gid = lane >> 2, tig = lane & 3;
   if (J == I) {
-    float *dA = reinterpret_cast<float *>(base + lay.off_diagA) + (size_t)I * kBlk * kBlk;
-    float *dB = reinterpret_cast<float *>(base + lay.off_diagB) + (size_t)I * kBlk * kBlk;
+    // fp64 push tables [ci][cj] = weight of sweep column ci for the later column cj of the same block
     double *pA = reinterpret_cast<double *>(base + lay.off_pushA) + (size_t)I * kBlk * kBlk;
     double *pB = reinterpret_cast<double *>(base + lay.off_pushB) + (size_t)I * kBlk * kBlk;
     for (int r = warp; r < kBlk; r += 4) {
-      // fp32 [cj][ci] = weight of in-block predecessor ci for cell cj (sweep order; zero for ci >= cj)
-      dA[r * kBlk + lane] = tile[lane][r];                                   // P'[ci][cj]
-      dB[r * kBlk + lane] = tile[kBlk - 1 - r][kBlk - 1 - lane];              // P'[31-cj][31-ci]
-      // fp64 push tables [ci][cj] = weight of sweep column ci for the later column cj
       pA[r * kBlk + lane] = (double)tile[r][lane];                            // P'[ci][cj]
       pB[r * kBlk + lane] = (double)tile[kBlk - 1 - lane][kBlk - 1 - r];      // P'[31-cj][31-ci]
     }
-  } else if (fmt == 1) {
+  } else {
     // canonical K-major core-matrix layout of tcgen05 (dag_dp4.cu): [plane hi|lo][k-core][n = 32][8 bf16 along K];
     // alpha direction: K = source, N = destination; beta direction: K = destination, N = source
     uint4 *tA = reinterpret_cast<uint4 *>(base + lay.off_tilesA + lay.idxA(I, J) * kTileBytes);
@@ -114,34 +99,10 @@ dag_tiles_kernel(const float *__restrict__ links, const int64_t *__restrict__ ol
       tA[kc * 32 + n] = ha; tA[128 + kc * 32 + n] = la;
       tB[kc * 32 + n] = hb; tB[128 + kc * 32 + n] = lb;
     }
-  } else {
-    uint4 *tA = reinterpret_cast<uint4 *>(base + lay.off_tilesA + lay.idxA(I, J) * kTileBytes);
-    uint4 *tB = reinterpret_cast<uint4 *>(base + lay.off_tilesB + lay.idxB(I, J) * kTileBytes);
-    auto bopA = [&](int k, int n) { return tile[k][n]; };  // K = source, N = destination
-    auto bopB = [&](int k, int n) { return tile[n][k]; };  // K = destination, N = source
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int q = warp * 2 + u;  // 4 warps x 2 <-> 8 units
-      const int qq = q & 3, ks = qq >> 1, nt0 = 2 * (qq & 1);
-      uint4 ua, ub;
-      if (q < 4) {
-        ua.x = frag_reg<false>(bopA, ks, nt0, 0, gid, tig); ua.y = frag_reg<false>(bopA, ks, nt0, 1, gid, tig);
-        ua.z = frag_reg<false>(bopA, ks, nt0 + 1, 0, gid, tig); ua.w = frag_reg<false>(bopA, ks, nt0 + 1, 1, gid, tig);
-        ub.x = frag_reg<false>(bopB, ks, nt0, 0, gid, tig); ub.y = frag_reg<false>(bopB, ks, nt0, 1, gid, tig);
-        ub.z = frag_reg<false>(bopB, ks, nt0 + 1, 0, gid, tig); ub.w = frag_reg<false>(bopB, ks, nt0 + 1, 1, gid, tig);
-      } else {
-        ua.x = frag_reg<true>(bopA, ks, nt0, 0, gid, tig); ua.y = frag_reg<true>(bopA, ks, nt0, 1, gid, tig);
-        ua.z = frag_reg<true>(bopA, ks, nt0 + 1, 0, gid, tig); ua.w = frag_reg<true>(bopA, ks, nt0 + 1, 1, gid, tig);
-        ub.x = frag_reg<true>(bopB, ks, nt0, 0, gid, tig); ub.y = frag_reg<true>(bopB, ks, nt0, 1, gid, tig);
-        ub.z = frag_reg<true>(bopB, ks, nt0 + 1, 0, gid, tig); ub.w = frag_reg<true>(bopB, ks, nt0 + 1, 1, gid, tig);
-      }
-      tA[q * 32 + lane] = ua;
-      tB[q * 32 + lane] = ub;
-    }
   }
 }
 
-int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl, int fmt,
+int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, int B, int M, int L, int Tl,
                     cudaStream_t st) {
   TileLayout lay = TileLayout::make(L, M);
   {
@@ -152,7 +113,7 @@ int launch_dag_prep(const float *links, const int64_t *olen, void *workspace, in
   {
     const int nd = min(lay.NB, band_blocks(Tl) + 1);
     dim3 grid(nd, lay.NB, B);
-    dag_tiles_kernel<<<grid, 128, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay, fmt);
+    dag_tiles_kernel<<<grid, 128, 0, st>>>(links, olen, (unsigned char *)workspace, L, Tl, lay);
     DAGB200_CHECK_LAUNCH("dag_tiles_kernel");
   }
   return 0;
