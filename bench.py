@@ -11,10 +11,19 @@ One "step" = one dag_loss forward (alpha+beta) + one dag_loss backward (grad_mat
 inputs resident in HBM.  A DP cell is one (b, t, j) of the padded B x M x L lattice; value = cells/s over all ranks.
 The step's working set (1.27 GB algorithmic) is ~10x the 126 MB L2, so no explicit L2 flush is needed.
 
+Multi-GPU (torchrun, one rank per GPU): utterances are sharded (B per GPU, weak scaling), no collective inside the
+DP; every step additionally carries the trainer's gradient exchange -- ONE NCCL all-reduce of a 300 MB fp32 buffer
+pre-divided by the world size (fairseq legacy_distributed_data_parallel.py:76-165), issued on a side stream right
+after the backward kernels so that it overlaps the next step's kernels (at most one exchange in flight; the step
+that follows waits for it before starting its own).  `collective` reports its stand-alone duration and the step
+time with the exchange fully exposed; `parts.no_collective` keeps the replica-only number.
+
 Prints ONE JSON line (rank 0).  Extra objects: roofline (dominant kernel, HBM bound, measured peak from
-MEASURED_PEAKS.json), cpu_baseline (CPU oracle = C port of the reference arithmetic, all host threads, bounded
-sample), e2e (same metric through the public operator API with pinned HOST buffers, H2D/D2H inside the timed
-region), clocks (NVML samples during the timed region), parts (other kernels of the path, informational).
+MEASURED_PEAKS.json, plus the tensor-core roofline of the same kernel), cpu_baseline (CPU oracle = C port of the
+reference arithmetic, all host threads, bounded sample), e2e (same metric through the public operator API with
+pinned HOST buffers, H2D/D2H inside the timed region), clocks (NVML samples during the timed region), parts (other
+kernels of the path, the banded T=32 and tuner-family shapes, and the UNMODIFIED reference CUDA kernels of
+oracle/_ref timed on the same tensors in the same run; informational).
 """
 import argparse
 import importlib
@@ -47,6 +56,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parts", action="store_true", help="skip the informational per-kernel parts")
+    ap.add_argument("--grad-mb", type=float, default=300.0, help="size of the gradient all-reduce buffer (MB, fp32); N>1 only")
     return ap.parse_args()
 
 
@@ -56,15 +66,32 @@ def algorithmic_bytes(B, M, L, T):
             "viterbi": 4 * (N + E) + 4 * B * L}
 
 
+def edge_relaxations(B, M, L, T):
+    """R = sum_b sum_{t>=1} sum_{j=t}^{L-1} min(j, T) at full lengths."""
+    r = 0
+    for t in range(1, M):
+        # sum_{j=t}^{L-1} min(j, T)
+        lo = t
+        if lo <= T:
+            hi = min(T, L - 1)
+            r += (lo + hi) * (hi - lo + 1) // 2
+            r += T * max(0, L - 1 - hi)
+        else:
+            r += T * (L - lo)
+    return r * B
+
+
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, source).  The step is a long back-to-back kernel sequence: sustained figure."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), \
+                "measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -147,6 +174,7 @@ def cpu_baseline(args, T, with_torch_path=True):
     `cpu_sample` utterances of the same workload; optionally also the torch restatement of torch_dag_loss."""
     import numpy as np
     from oracle import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: size the pool ourselves
     Bs = max(1, min(args.cpu_sample, args.batch))
     L, M = args.prelen, args.tarlen
     match, links, olen, tlen = oracle.make_lattice(Bs, L, M, T, seed=1234, ragged=False)
@@ -172,12 +200,47 @@ def cpu_baseline(args, T, with_torch_path=True):
             torch.autograd.grad(loss.sum(), [m, dense])
             dt2 = time.perf_counter() - t0
             out["torch_path"] = {"value": M * L / dt2, "unit": UNIT, "threads": torch.get_num_threads(),
+                                 "kind": "port (this repo's torch restatement of torch_dag_loss, not the reference file)",
                                  "sample": "1 utterance, dense-links torch restatement of torch_dag_loss + autograd "
                                            "(the reference's CPU algorithm, dag_loss.py:325-366), %.2f s" % dt2}
             del lk
         except Exception as e:  # pragma: no cover
             out["torch_path"] = {"error": str(e)[:200]}
     return out
+
+
+def reference_cuda_times(torch, k, match, links, olen, tlen, go, B, L, M, V, timeit, n=10):
+    """Times the reference's own CUDA kernels (the compiled, unmodified extension) as a baseline leg, like cpu_baseline."""
+    import glob
+    import importlib.util
+    so = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "dag_loss_fn*.so")))
+    if not so:
+        return {"unavailable": "oracle/_ref/dag_loss_fn.so not present (built from /root/reference by oracle/build_ref.py)"}
+    try:
+        spec = importlib.util.spec_from_file_location("dag_loss_fn", so[0])
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        dev = match.device
+        out = {"iterations": n, "so": os.path.relpath(so[0], ROOT)}
+        a0, b0 = ref.dag_loss(match, links, olen, tlen, True, 1)
+        a1, b1 = k.dag_loss(match, links, olen, tlen, True, 1)
+        out["loss_max_rel_diff"] = float(((b0[:, 0, 0] - b1[:, 0, 0]).abs() / b0[:, 0, 0].abs()).max())
+        out["ref_fwd_ms"] = timeit(lambda: ref.dag_loss(match, links, olen, tlen, True, 1), n)
+        out["new_fwd_ms"] = timeit(lambda: k.dag_loss(match, links, olen, tlen, True, 1), n)
+        out["ref_bwd_ms"] = timeit(lambda: ref.dag_loss_backward(go, a0, b0, match, links, olen, tlen, 2, 2), n)
+        out["new_bwd_ms"] = timeit(lambda: k.dag_loss_backward(go, a1, b1, match, links, olen, tlen, 2, 2), n)
+        out["ref_viterbi_ms"] = timeit(lambda: ref.dag_best_alignment(match, links, olen, tlen, 1), n)
+        out["new_viterbi_ms"] = timeit(lambda: k.dag_best_alignment(match, links, olen, tlen, 1, want_alpha=False), n)
+        del a0, b0, a1, b1
+        for name, dt in (("fp16", torch.float16), ("fp32", torch.float32)):
+            x = (torch.randn(B, L, V, device=dev) * 2).to(dt)
+            idx = torch.randint(4, V, (B, M), device=dev).unsqueeze(1).expand(-1, L, -1)
+            out["ref_gather_%s_ms" % name] = timeit(lambda: ref.logsoftmax_gather(x, idx, True), n)
+            out["new_gather_%s_ms" % name] = timeit(lambda: k.logsoftmax_gather(x, idx, True), n)
+            del x, idx
+        return out
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)[:300]}
 
 
 def run_reference(args):
@@ -188,6 +251,7 @@ def run_reference(args):
         return 0
     import numpy as np
     from oracle import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: size the pool ourselves
     L, M = args.prelen, args.tarlen
     T = args.translen or (L - 1)
     Bs = max(1, min(args.cpu_sample, args.batch))
@@ -223,7 +287,10 @@ def workload_config(args, T):
     return {"workload": "C2 dag_loss fwd+bwd: B=%d utterances/GPU, L=%d vertices, M=%d targets, T=%d transitions, "
                         "full lengths, fp32" % (args.batch, args.prelen, args.tarlen, T),
             "global_batch": args.batch * args.gpus, "prelen": args.prelen, "tarlen": args.tarlen, "translen": T,
-            "vocab": args.vocab, "parallelism": "dp%d (utterance-sharded, no data-path collective)" % args.gpus,
+            "vocab": args.vocab,
+            "parallelism": ("dp1 (single GPU)" if args.gpus == 1 else
+                            "dp%d: utterance-sharded, no collective inside the DP; one NCCL all-reduce of a %.0f MB fp32 "
+                            "gradient buffer per step (side stream, overlaps the next step's kernels)" % (args.gpus, args.grad_mb)),
             "l2": "inputs larger than L2 (1.27 GB touched per step vs 126 MB L2); no flush"}
 
 
@@ -258,45 +325,91 @@ def main():
     k = ops.get_dag_kernel()
     match, links, olen, tlen, go = make_inputs(torch, dev, B, L, M, T, V, 1234 + rank)
     bytes_ = algorithmic_bytes(B, M, L, T)
-    peak_gbs, peak_src = measured_peaks()
+    peak_gbs, peak_tf, peak_src = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the trainer's gradient exchange (N > 1 only): one flat fp32 buffer, pre-divided, all-reduced on a side stream
+    from daspeech_b200.dist import FlatGradAllReduce
+    exchange = FlatGradAllReduce(int(args.grad_mb * 1e6 / 4), torch.float32, dev) if world > 1 else None
+
     def step():
         alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
         gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
         return alpha, beta, gm, gl
 
+    def run_steps(n, overlap=True, with_exchange=True):
+        """n steps; with the exchange of step i overlapping the kernels of step i+1 (overlap) or fully exposed."""
+        out = None
+        for _ in range(n):
+            alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
+            gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+            if exchange is not None and with_exchange:
+                exchange.finish()          # the previous step's exchange (a no-op the first time)
+                exchange.start()           # this step's gradients: side stream, after the backward kernels
+                if not overlap:
+                    exchange.finish()
+            out = (alpha, beta, gm, gl)
+        if exchange is not None and with_exchange:
+            exchange.finish()
+        return out
+
     # warm-up with exactly the allocation pattern of the timed loop (same names kept alive), so that the caching
     # allocator is in steady state and no cudaMalloc (a device-wide sync) lands inside the timed region
-    for _ in range(W):
-        alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
-        gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+    alpha, beta, gm, gl = run_steps(W)
     barrier()
     # ---- timed region: exactly K steps -------------------------------------------------------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
-    for s in range(K):
-        alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
-        gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+    alpha, beta, gm, gl = run_steps(K)
     ev[1].record()
-    # The K steps are now queued on the stream (the host enqueues a step in < 0.1 ms, the GPU needs ~2 ms for it).
+    # The K steps are now queued on the stream (the host enqueues a step in < 0.1 ms, the GPU needs ~1 ms for it).
     # Clocks / throttle reasons are sampled while the GPU works through them: NVML queries take the driver lock, so
     # sampling WHILE launching would stall the launches and show up as idle gaps between kernels.
     with ClockSampler(local) as clk:
         barrier()
-    elapsed_ms = ev[0].elapsed_time(ev[1])
-    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    ms_per_step = elapsed_ms / K
+
+    def max_ms(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_per_step = max_ms(ev[0].elapsed_time(ev[1])) / K
     cells = B * M * L * world
     value = cells / (ms_per_step * 1e-3)
     loss_check = float(beta[:, 0, 0].float().mean().item())
+
+    def timed(fn, n):
+        barrier()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(n)
+        b2.record()
+        barrier()
+        return max_ms(a.elapsed_time(b2)) / n
+
+    collective = None
+    if exchange is not None:
+        kc = max(3, min(K, 10))
+        exposed_ms = timed(lambda n: run_steps(n, overlap=False), kc)
+        replica_ms = timed(lambda n: run_steps(n, with_exchange=False), kc)
+
+        def only_exchange(n):
+            for _ in range(n):
+                exchange.start()
+                exchange.finish()
+        only_exchange(2)
+        ar_ms = timed(only_exchange, kc)
+        nbytes = exchange.buffer.numel() * 4
+        collective = {"kind": "nccl all_reduce(sum) of one flat fp32 gradient buffer, pre-divided by the world size",
+                      "bytes": nbytes, "collective_ms": ar_ms,
+                      "busbw_gbs": nbytes * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9,
+                      "step_ms_overlapped": ms_per_step, "step_ms_exposed": exposed_ms, "step_ms_no_collective": replica_ms,
+                      "reference": "fairseq legacy_distributed_data_parallel.py:76-165 via trainer.py:928"}
 
     # ---- per-kernel durations: CUDA events recorded by the library on the launch stream around each of its
     # kernels (dagb200_set_profile), averaged over a few extra steps right after the timed region -----------
@@ -329,14 +442,24 @@ def main():
     except Exception:
         pass
     ach = kbytes[dom_name] / (dom_ms * 1e-3) / 1e9
+    # tensor-core work of the blocked kernels: every edge relaxation is one MAC, executed as three
+    # bf16 MMAs (hi*hi, lo*hi, hi*lo); alpha and beta each relax R edges, grad_links contracts the same R products
+    R = edge_relaxations(B, M, L, T)
+    kflop = {"dag_alpha_beta_tcgen05_kernel": 2 * R * 3 * 2, "grad_links_planes_kernel": R * 3 * 2}
+    compute = {"flop": kflop[dom_name], "achieved": kflop[dom_name] / (dom_ms * 1e-3) / 1e12, "peak": peak_tf,
+               "unit": "TFLOP/s", "frac": kflop[dom_name] / (dom_ms * 1e-3) / 1e12 / peak_tf,
+               "edge_relaxations_per_pass": R,
+               "note": "algorithmic bf16x3 tensor flop of the kernel over the measured sustained bf16 peak; the kernel is "
+                       "bound by neither roofline but by its serial fp64 chain and the single-thread MMA issue path"}
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s", "frac": ach / peak_gbs,
-                "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms,
+                "traffic": traffic, "kernel": dom_name, "kernel_ms": dom_ms, "compute": compute,
                 "algorithmic_bytes_per_launch": kbytes[dom_name], "peak_source": peak_src,
                 "kernels_ms": kern,
                 "step": {"algorithmic_bytes": bytes_["fwd_bwd"], "ms": ms_per_step,
                          "achieved": bytes_["fwd_bwd"] / (ms_per_step * 1e-3) / 1e9,
                          "frac": bytes_["fwd_bwd"] / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
                          "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                         "compute_frac": 3 * R * 3 * 2 / (ms_per_step * 1e-3) / 1e12 / peak_tf,
                          "note": "HBM roofline of the whole fwd+bwd step; the recurrences are tensor/issue bound "
                                  "at T=L-1 (DESIGN.md section 5)"}}
 
@@ -376,12 +499,12 @@ def main():
     e2e_run(e2e_k)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_k
+    e2e_ms = max_ms(e0.elapsed_time(e1)) / e2e_k
     e2e = {"value": cells / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_ms, "steps": e2e_k, "host_bound_to_gpu_numa_node": numa_bound,
+           "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9,
+           "limiter": "host->device copy of the step's inputs (%.0f MB per rank and step over PCIe; the kernels of a step "
+                      "take %.2f ms and hide behind it)" % (h2d / 1e6, ms_per_step),
            "api": "daspeech_b200.dag_loss(match_all, links, output_length, target_length) + .backward(), every step's "
                   "inputs copied from pinned host memory (DevicePrefetcher: the copy of step i+1 overlaps step i), "
                   "per-utterance loss read back"}
@@ -449,6 +572,25 @@ def main():
                                     "frac": by_g / ms_g / 1e6 / peak_gbs, "torch_ops_ms": ms_gt}
         del mm, keepm, prevm
 
+        # the banded secondary configuration (T = 32, the reference tuner's setting) and the tuner's shape family
+        def fwd_bwd(B_, L_, M_, T_, n=10):
+            m_, lk_, ol_, tl_, go_ = make_inputs(torch, dev, B_, L_, M_, T_, V, 99)
+
+            def f():
+                a_, b_ = k.dag_loss(m_, lk_, ol_, tl_, True, 1)
+                k.dag_loss_backward(go_, a_, b_, m_, lk_, ol_, tl_, 2, 2)
+            ms = timeit(f, n)
+            by = algorithmic_bytes(B_, M_, L_, T_)["fwd_bwd"]
+            vit = timeit(lambda: k.dag_best_alignment(m_, lk_, ol_, tl_, 1, want_alpha=False), n) if (M_ - 1) * T_ + 1 >= L_ else None
+            return {"shape": {"B": B_, "L": L_, "M": M_, "T": T_}, "fwd_bwd_ms": ms, "cells_per_s": B_ * M_ * L_ / (ms * 1e-3),
+                    "algorithmic_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak_gbs, "dag_best_alignment_ms": vit}
+        parts["c2_T32"] = fwd_bwd(B, L, M, 32)
+        parts["tuner_shape"] = fwd_bwd(81, 400, 50, 32)
+
+        # the GPU reference bar: the UNMODIFIED reference CUDA kernels, compiled from
+        # /root/reference by oracle/build_ref.py into oracle/_ref/dag_loss_fn.so, on the same tensors in the same run
+        parts["reference_cuda"] = reference_cuda_times(torch, k, match, links, olen, tlen, go, B, L, M, V, timeit)
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -457,6 +599,10 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, T),
                 "utt_per_sec": B * world / (ms_per_step * 1e-3), "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": 5 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
+        if collective is not None:
+            line["collective"] = collective
+            parts["no_collective"] = {"ms_per_step": collective["step_ms_no_collective"],
+                                      "value": cells / (collective["step_ms_no_collective"] * 1e-3), "unit": UNIT}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, T)
         print(json.dumps(line), flush=True)

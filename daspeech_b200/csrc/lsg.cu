@@ -471,6 +471,35 @@ lsg_bwd_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int64_t i
   }
 }
 
+// backward for rows beyond the shared-memory staging limits (V > ~51 k elements; > 25 k in fp64): no vocabulary
+// limit, as the reference's mul_ + scatter_add_ (dag_loss.py:294-295).  The row is scaled in place in global memory,
+// then the S targets are added with global atomics in the row's dtype (one rounding per addition, as scatter_add_).
+template <typename T, typename C>
+__global__ void __launch_bounds__(kLsgThreads)
+lsg_bwd_global_kernel(T *__restrict__ probs, const int64_t *__restrict__ idx, int64_t isb, int64_t isl, int64_t iss,
+                      const C *__restrict__ gout, int64_t gsb, int64_t gsl, int64_t gss, int L, int V, int S, int64_t rows) {
+  __shared__ C red[kLsgThreads / 32];
+  __shared__ C bcast;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / L), l = (int)(row % L);
+    T *x = probs + row * (int64_t)V;
+    const C *gb = gout + b * gsb + l * gsl;
+    C part = 0;
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) part += gb[s * gss];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) { C t = 0; for (int w = 0; w < kLsgThreads / 32; w++) t += red[w]; bcast = t; }
+    __syncthreads();
+    const C neg = (C)(T)(-bcast);
+    for (int c = threadIdx.x; c < V; c += kLsgThreads) x[c] = (T)((C)x[c] * neg);
+    __syncthreads();   // the scaled row is visible to the whole CTA before the scatter
+    const int64_t *ib = idx + b * isb + l * isl;
+    for (int s = threadIdx.x; s < S; s += kLsgThreads) atomicAdd(&x[ib[s * iss]], (T)gb[s * gss]);
+    __syncthreads();
+  }
+}
+
 // vectorised backward for 16-bit / fp32 rows with V % kElems == 0
 template <typename T>
 __global__ void __launch_bounds__(kLsgThreads)
@@ -875,7 +904,12 @@ static int lsg_bwd_dispatch16(T *probs, const int64_t *idx, int64_t isb, int64_t
   const int64_t rows = (int64_t)B * L;
   const bool aligned = (V % E == 0) && ((reinterpret_cast<uintptr_t>(probs) & 15) == 0);
   const size_t smem = (size_t)(V + 16) * sizeof(float);
-  if (smem > 200 * 1024) { set_error("logsoftmax_gather_backward: V=%d too large for the staged row", V); return DAGB200_ELIMIT; }
+  if (smem > 200 * 1024) {   // the fp32 copy of a row does not fit in shared memory: global-memory backward, any V
+    const unsigned grid = (unsigned)(rows < (int64_t)sm_count() * 8 ? rows : (int64_t)sm_count() * 8);
+    lsg_bwd_global_kernel<T, float><<<grid, kLsgThreads, 0, st>>>(probs, idx, isb, isl, iss, gout, gsb, gsl, gss, L, V, S, rows);
+    DAGB200_CHECK_LAUNCH("lsg_bwd_global_kernel");
+    return 0;
+  }
   static const bool no_tma = getenv("DAGB200_LSG_NOTMA") != nullptr;
   const int need = (V / E + kLsgThreads - 1) / kLsgThreads;
   // 16-bit rows with the criterion's expanded (stride-0) index view: scatter applied in registers
@@ -985,9 +1019,13 @@ extern "C" int dagb200_logsoftmax_gather_backward(void *probs, int dtype, const 
     case DAGB200_F64: {
       const int64_t rows = (int64_t)B * L;
       const size_t smem = (size_t)V * sizeof(double);
-      DAGB200_CHECK_ARG(smem <= 200 * 1024, DAGB200_ELIMIT, "logsoftmax_gather_backward: V=%d too large (fp64)", V);
-      cudaFuncSetAttribute(lsg_bwd_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       const unsigned grid = (unsigned)(rows < (int64_t)sm_count() * 8 ? rows : (int64_t)sm_count() * 8);
+      if (smem > 200 * 1024) {
+        lsg_bwd_global_kernel<double, double><<<grid, kLsgThreads, 0, st>>>((double *)probs, idx, isb, isl, iss, (const double *)gout, gsb, gsl, gss, L, V, S, rows);
+        DAGB200_CHECK_LAUNCH("lsg_bwd_global_kernel<double>");
+        return 0;
+      }
+      cudaFuncSetAttribute(lsg_bwd_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       lsg_bwd_kernel<double, double><<<grid, kLsgThreads, smem, st>>>((double *)probs, idx, isb, isl, iss, (const double *)gout, gsb, gsl, gss, L, V, S, rows);
       DAGB200_CHECK_LAUNCH("lsg_bwd_kernel<double>");
       return 0;

@@ -17,6 +17,7 @@ without the built library they raise.  The torch_* functions are independent re-
 they are part of the exported surface; the CUDA operators never route through them.
 """
 import os
+import warnings
 from typing import Tuple
 
 import torch
@@ -77,6 +78,40 @@ class _DagKernel:
             raise RuntimeError("You need GPU to use the custom cuda operations")
         self.lib = _lib.load()
         self._scratch = {}
+        self._pending = []      # (what, pinned host copy of the per-sample status, event) of earlier calls
+
+    # ---- per-sample device status (the reference's CUDA_KERNEL_ASSERTs, dag_loss.cu:68-69, dag_best_alignment.cu:67-70,118)
+    # The status words are always produced (B int32).  DAGB200_DEBUG=1 checks them synchronously and raises; otherwise
+    # they are copied to pinned host memory without a sync and inspected at the next operator call (or by
+    # `check_pending_status()`), where a violation becomes a RuntimeWarning naming the sample.
+    def _track_status(self, what, status):
+        if _DEBUG:
+            _check_status(status)
+            return
+        host = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+        host.copy_(status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending.append((what, host, ev))
+
+    def check_pending_status(self, wait=False):
+        keep = []
+        for what, host, ev in self._pending:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                keep.append((what, host, ev))
+                continue
+            bad = host.nonzero()
+            if bad.numel():
+                b = int(bad[0])
+                warnings.warn("%s: sample %d: %s (%d sample(s) affected; outputs are -inf / -1 for them)" % (
+                    what, b, _STATUS_TEXT.get(int(host[b]), "device status %d" % int(host[b])), bad.numel()), RuntimeWarning)
+        self._pending = keep
+
+    def release_workspaces(self):
+        """Drop the cached per-(device, stream) scratch buffers (~400 MB each at the C2 shape)."""
+        self._scratch.clear()
 
     def _workspace(self, nbytes, device):
         """Per-(device, stream) scratch for the blocked kernels, grown on demand and kept across calls: the
@@ -101,6 +136,8 @@ class _DagKernel:
         _check(links.is_cuda, "links must be a CUDA tensor")
         _check(output_length.is_cuda, "output_length must be a CUDA tensor")
         _check(target_length.is_cuda, "target_length must be a CUDA tensor")
+        _check(links.device == match_all.device and output_length.device == match_all.device and
+               target_length.device == match_all.device, "match_all, links and the lengths must be on the same device")
         _check(match_all.dim() == 3, "match_all dim != 3")
         _check(links.dim() == 3, "links dim != 3")
         _check(output_length.dim() == 1, "output_length dim != 3")
@@ -123,9 +160,10 @@ class _DagKernel:
         target_length = target_length.contiguous()
         alpha = torch.empty((bsz, tarlen, prelen), dtype=match_all.dtype, device=match_all.device)
         beta = torch.empty_like(alpha)
-        status = torch.empty(bsz, dtype=torch.int32, device=match_all.device) if _DEBUG else None
+        self.check_pending_status()
+        status = torch.empty(bsz, dtype=torch.int32, device=match_all.device)
         nbytes = 0
-        if EXACT_LOG_DOMAIN is False and match_all.dtype == torch.float32:
+        if not EXACT_LOG_DOMAIN and match_all.dtype == torch.float32:
             nbytes = int(self.lib.dagb200_dag_loss_workspace_bytes(bsz, tarlen, prelen, translen))
         workspace = self._workspace(nbytes, match_all.device)
         self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
@@ -135,7 +173,8 @@ class _DagKernel:
                                            bsz, tarlen, prelen, translen, int(bool(require_gradient)), int(config),
                                            _ptr(workspace), nbytes, _ptr(status), _stream())
         _lib.check(rc, "dag_loss")
-        _check_status(status)
+        if bsz:
+            self._track_status("dag_loss", status)
         return alpha, beta
 
     def dag_loss_backward(self, grad_output, alpha, beta, match_all, links, output_length, target_length,
@@ -145,10 +184,12 @@ class _DagKernel:
         grad_output = grad_output.to(match_all.dtype).contiguous()
         match_all = match_all.contiguous()
         links = links.contiguous()
+        output_length = output_length.contiguous()
+        target_length = target_length.contiguous()
         grad_match_all = torch.empty_like(alpha)
         grad_links = torch.empty((bsz, prelen, translen), dtype=match_all.dtype, device=match_all.device)
         nbytes = 0
-        if EXACT_LOG_DOMAIN is False and match_all.dtype == torch.float32:
+        if not EXACT_LOG_DOMAIN and match_all.dtype == torch.float32:
             nbytes = int(self.lib.dagb200_dag_loss_backward_workspace_bytes(bsz, tarlen, prelen, translen))
         workspace = self._workspace(nbytes, match_all.device)
         self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
@@ -173,7 +214,8 @@ class _DagKernel:
         path = torch.empty((bsz, prelen), dtype=torch.int32, device=dev)
         nbytes = int(self.lib.dagb200_best_alignment_workspace_bytes(bsz, tarlen, prelen, translen))
         workspace = self._workspace(max(nbytes, 1), dev)
-        status = torch.empty(bsz, dtype=torch.int32, device=dev) if _DEBUG else None
+        self.check_pending_status()
+        status = torch.empty(bsz, dtype=torch.int32, device=dev)
         self.lib.dagb200_set_exact(int(bool(EXACT_LOG_DOMAIN)))
         with torch.cuda.device(dev):
             rc = self.lib.dagb200_dag_best_alignment(_ptr(match_all), _ptr(links), _ptr(output_length),
@@ -181,7 +223,8 @@ class _DagKernel:
                                                      _DTYPE_CODE[match_all.dtype], bsz, tarlen, prelen, translen,
                                                      int(config), _ptr(workspace), nbytes, _ptr(status), _stream())
         _lib.check(rc, "dag_best_alignment")
-        _check_status(status)
+        if bsz:
+            self._track_status("dag_best_alignment", status)
         return alpha, path
 
     def logsoftmax_gather(self, word_ins_out, select_idx, require_gradient, want_argmax=False):

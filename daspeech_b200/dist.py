@@ -3,6 +3,10 @@ collective inside the DP (every lattice is independent -- SURVEY.md section 8(e)
 ones the reference's trainer performs around the criterion: summing the logging scalars
 (fairseq trainer.py:1469 -> distributed/utils.py:668) and, for timing, a MAX over ranks.
 
+The data-parallel step itself has one more collective, the gradient all-reduce of the trainer
+(fairseq legacy_distributed_data_parallel.py:76-165: one flat buffer, pre-divided by the world size, all_reduce):
+`FlatGradAllReduce` below is that exchange, issued on a side stream so that it overlaps the tail of the backward pass.
+
 Works with backend "nccl" on GPUs and "gloo" on CPU (used by the world_size-2 tests).
 """
 from typing import Dict, Sequence, Tuple
@@ -35,7 +39,8 @@ def sum_stats(stats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """One flat all-reduce(SUM) of the per-rank logging scalars (loss sum, token counts, invalid sentences)."""
     rank, ws = world()
     keys = sorted(stats)
-    flat = torch.stack([stats[k].detach().to(torch.float64).reshape(()) for k in keys])
+    dev = next((v.device for v in stats.values() if v.is_cuda), torch.device("cpu"))   # NCCL reduces device tensors only
+    flat = torch.stack([stats[k].detach().to(device=dev, dtype=torch.float64).reshape(()) for k in keys])
     if ws > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     return {k: flat[i] for i, k in enumerate(keys)}
@@ -58,6 +63,43 @@ def dag_nll_sharded(loss_fn, match_all, links, output_length, target_length):
     loss = loss_fn(m, lk, ol, tl)
     invalid = loss.isinf().logical_or(loss.isnan())
     loss = loss.masked_fill(invalid, 0)
-    stats = sum_stats({"nll_sum": -(loss / tl).sum(), "nsentences": torch.tensor(float(loss.shape[0])),
+    stats = sum_stats({"nll_sum": -(loss / tl).sum(), "nsentences": loss.new_tensor(float(loss.shape[0])),
                        "invalid_nsentences": invalid.sum(), "ntokens": tl.sum()})
     return stats["nll_sum"] / stats["nsentences"], loss, stats
+
+
+class FlatGradAllReduce:
+    """The trainer's gradient exchange for one update (fairseq legacy_distributed_data_parallel.py:108-165,
+    trainer.py:928,946): ONE flat buffer holding all gradients, divided by the world size, summed over ranks.
+
+    `start()` is called where the backward pass has produced the gradients that go into the buffer; it makes a side
+    stream wait for the producer stream, scales and all-reduces there, so whatever the producer stream runs next (the
+    rest of the backward pass, the next step's forward) overlaps the exchange.  `finish()` makes the current stream
+    wait for the result (the optimizer step would read it).  On CPU tensors (gloo tests) both are synchronous."""
+
+    def __init__(self, numel: int, dtype=torch.float32, device=None):
+        self.buffer = torch.zeros(numel, dtype=dtype, device=device)
+        self.cuda = self.buffer.is_cuda
+        self.side = torch.cuda.Stream(device=self.buffer.device) if self.cuda else None
+        self._done = None
+
+    def start(self):
+        _, ws = world()
+        if not self.cuda:
+            if ws > 1:
+                self.buffer.div_(ws)
+                dist.all_reduce(self.buffer)
+            return
+        self.side.wait_stream(torch.cuda.current_stream(self.buffer.device))
+        with torch.cuda.stream(self.side):
+            if ws > 1:
+                self.buffer.div_(ws)
+                dist.all_reduce(self.buffer)
+            self._done = torch.cuda.Event()
+            self._done.record(self.side)
+
+    def finish(self):
+        if self.cuda and self._done is not None:
+            torch.cuda.current_stream(self.buffer.device).wait_event(self._done)
+            self._done = None
+        return self.buffer

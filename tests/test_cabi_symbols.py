@@ -69,3 +69,15 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdagb200.so")
     with pytest.raises(RuntimeError, match="no CPU/torch fallback"):
         _lib.load()
+
+
+def test_pybind_shim_exports_the_reference_entry_points():
+    """daspeech_b200/csrc/dag_loss_fn.so: the module a maintainer returns from get_dag_kernel() (INTEGRATION.md option B)
+    must expose exactly the four callables of DASpeech/custom_ops/dag_loss.cpp:24-29 (import only; no GPU here)."""
+    from daspeech_b200.csrc import build_shim
+    build_shim.build()
+    mod = build_shim.load()
+    names = sorted(n for n in dir(mod) if not n.startswith("_"))
+    assert names == ["dag_best_alignment", "dag_loss", "dag_loss_backward", "logsoftmax_gather"]
+    for n in names:
+        assert callable(getattr(mod, n))

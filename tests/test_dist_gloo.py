@@ -36,8 +36,13 @@ def _worker(rank, ws, port, B, out):
     lo, hi = ddist.shard_range(B, rank, ws)
     assert local.shape[0] == hi - lo
     t = ddist.max_over_ranks(float(rank + 1))
+    # the trainer's flat gradient exchange: pre-divided by the world size, summed -> the mean over ranks
+    ar = ddist.FlatGradAllReduce(1000, torch.float32)
+    ar.buffer.copy_(torch.arange(1000, dtype=torch.float32) * (rank + 1))
+    ar.start()
+    gmean = ar.finish().clone()
     if rank == 0:
-        torch.save({"mean": mean, "stats": stats, "tmax": t}, out)
+        torch.save({"mean": mean, "stats": stats, "tmax": t, "gmean": gmean}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,3 +76,4 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert int(got["stats"]["invalid_nsentences"]) == 1 and int(got["stats"]["nsentences"]) == B
     assert int(got["stats"]["ntokens"]) == int(tlen.sum())
     assert got["tmax"] == 2.0
+    assert torch.allclose(got["gmean"], torch.arange(1000, dtype=torch.float32) * 1.5)

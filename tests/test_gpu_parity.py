@@ -4,9 +4,12 @@ torch path (tests/golden/), and -- when oracle/_ref/ holds the prebuilt UNMODIFI
 the reference kernels themselves on the same tensors.
 
 Tolerances (BASELINE.json north_star): arg-max alignment indices bit-exact; fp32 loss within 1e-4 relative;
-fp32 gradients within 1e-4 of the tensor's scale (|g - g_ref|_inf <= 1e-4 * |g_ref|_inf).  At the full C2 shape
-fp32 log-domain arithmetic itself sits ~1-2e-4 from the fp64 truth (DESIGN.md "Numerics"), so there the bound is
-max(1e-4, 1.5 x the error of the fp32 restatement of the reference arithmetic) against the fp64 oracle.
+fp32 gradients ELEMENT-WISE: elem_err(g, g_ref) = max_i |g_i - ref_i| / max(|ref_i|, 1e-6 * max|ref|), i.e. a relative
+bound for every element within six decades of the largest one and the matching absolute bound below that floor
+(tiny posteriors count).  The bound is tol = max(1e-4, 1.5 x the same statistic of the oracle's fp32 build), both
+against the fp64 oracle: the lattices are fp32 tensors at the boundary, so |alpha|, |beta| ~ 1e3 carry an ulp of
+6e-5..1.2e-4 that no implementation can undercut (the reference tolerates rtol 1e-3 on the loss and torch.allclose
+defaults on the gradients, custom_ops/dag_loss.py:478,492-493).  DESIGN.md section 6 tabulates the bounds per shape.
 """
 import glob
 import importlib
@@ -40,6 +43,26 @@ def relerr(x, ref):
     ref = np.asarray(ref, dtype=np.float64)
     s = np.abs(ref).max()
     return float(np.abs(x - ref).max() / (s if s > 0 else 1.0))
+
+
+GRAD_FLOOR = 1e-6
+
+
+def elem_err(x, ref, floor=GRAD_FLOOR):
+    """max_i |x_i - ref_i| / max(|ref_i|, floor * max|ref|): element-wise relative error down to `floor` of the largest
+    element, absolute (at the floor's scale) below it."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    s = np.abs(ref).max()
+    if not s > 0:
+        return float(np.abs(x).max())
+    return float((np.abs(x - ref) / np.maximum(np.abs(ref), floor * s)).max())
+
+
+def grad_tol(ref32, truth):
+    """Element-wise bound for a gradient tensor: 1e-4, or 1.5 x what the reference's own fp32 arithmetic (oracle fp32
+    build) achieves on the same lattice against the fp64 truth, whichever is larger."""
+    return max(1e-4, 1.5 * elem_err(ref32, truth))
 
 
 def check_lattice_side_outputs(a, b, oa, ob, match, z):
@@ -84,8 +107,20 @@ def test_dag_loss_against_reference_golden(name, dtype):
         tol = max(tol, 1e-5)
     assert np.allclose(loss[fin], ref[fin], rtol=tol, atol=0)
     if "grad_match" in g:
-        assert relerr(gm, g["grad_match"]) <= tol
-        assert relerr(gl, g["grad_links"]) <= tol
+        tgm, tgl = g["grad_match"], g["grad_links"]
+        if name.endswith("fp32"):
+            # this golden was produced by the reference's torch path in fp32: element-wise the truth is the fp64 oracle
+            _, a64, b64 = oracle.dag_loss(g["match"], g["links"], g["olen"], g["tlen"], True, np.float64)
+            tgm, tgl = oracle.dag_loss_backward(g["grad_output"], a64, b64, g["match"], g["links"], g["olen"], g["tlen"], np.float64)
+            assert relerr(tgm, g["grad_match"]) <= 1e-4 and relerr(tgl, g["grad_links"]) <= 1e-4
+        etol_m = etol_l = 1e-9
+        if dtype == torch.float32:
+            _, a32, b32 = oracle.dag_loss(g["match"], g["links"], g["olen"], g["tlen"], True, np.float32)
+            gm32, gl32 = oracle.dag_loss_backward(g["grad_output"], a32, b32, g["match"], g["links"], g["olen"], g["tlen"], np.float32)
+            etol_m, etol_l = grad_tol(gm32, tgm), grad_tol(gl32, tgl)
+        em, el = elem_err(gm, tgm), elem_err(gl, tgl)
+        print("elem grad errors", em, el, "bounds", etol_m, etol_l)
+        assert em <= etol_m and el <= etol_l, (em, el, etol_m, etol_l)
     else:  # infeasible sample: zero gradients, never NaN (dag_loss.cu:395,463)
         assert np.isfinite(gm).all() and np.isfinite(gl).all()
         assert not gm[~fin].any() and not gl[~fin].any()
@@ -114,7 +149,7 @@ SHAPES = [
     (2, 352, 300, 351, True, 0.0),   # more than 256 target rows: two passes of the column-major recurrences
     (1, 640, 530, 639, False, 0.0),  # three passes, 17 row chunks (odd split between the Viterbi cluster CTAs)
     (2, 320, 290, 40, True, 0.1),    # two passes, banded transitions, forced emissions
-    (1, 2080, 24, 2079, False, 0.0), # 65 vertex blocks: beyond the shared memory of the tcgen05 / mma.sync recurrences (dp2 fallback)
+    (1, 2080, 24, 2079, False, 0.0), # 65 vertex blocks: beyond the shared memory of the tcgen05 recurrences (exact log-domain kernels)
 ]
 
 
@@ -129,18 +164,15 @@ def test_dag_loss_against_oracle(shape):
     fin = np.isfinite(ol64)
     assert np.array_equal(np.isfinite(loss), fin)
     assert np.allclose(loss[fin], ol64[fin], rtol=1e-4, atol=0)
-    tol_m = tol_l = 1e-4
-    if M > 128:
-        # lattice values ~1e3 carry an fp32 ulp of 6e-5..1.2e-4: the reference's own fp32 arithmetic (restated in the
-        # oracle's fp32 build) is then only accurate to ~1e-4, so the bar is relative to it (DESIGN.md "Numerics")
-        _, a32, b32 = oracle.dag_loss(match, links, olen, tlen, True, np.float32)
-        gm32, gl32 = oracle.dag_loss_backward(go, a32, b32, match, links, olen, tlen, np.float32)
-        tol_m = max(1e-4, 1.5 * relerr(np.where(fin[:, None, None], gm32, 0), np.where(fin[:, None, None], ogm, 0)))
-        tol_l = max(1e-4, 1.5 * relerr(np.where(fin[:, None, None], gl32, 0), np.where(fin[:, None, None], ogl, 0)))
-    em, el = relerr(gm, np.where(fin[:, None, None], ogm, 0)), relerr(gl, np.where(fin[:, None, None], ogl, 0))
-    print("grad errors", em, el, "tolerances", tol_m, tol_l)
-    assert em <= tol_m
-    assert el <= tol_l
+    _, a32, b32 = oracle.dag_loss(match, links, olen, tlen, True, np.float32)
+    gm32, gl32 = oracle.dag_loss_backward(go, a32, b32, match, links, olen, tlen, np.float32)
+    f3 = fin[:, None, None]
+    ogm, ogl = np.where(f3, ogm, 0), np.where(f3, ogl, 0)
+    tol_m, tol_l = grad_tol(np.where(f3, gm32, 0), ogm), grad_tol(np.where(f3, gl32, 0), ogl)
+    em, el = elem_err(gm, ogm), elem_err(gl, ogl)
+    print("elem grad errors", em, el, "bounds", tol_m, tol_l)
+    assert em <= tol_m, (em, tol_m)
+    assert el <= tol_l, (el, tol_l)
     check_lattice_side_outputs(alpha.cpu().numpy(), beta.cpu().numpy(), oa, ob, match, ol64)
 
 
@@ -172,7 +204,7 @@ def test_dag_loss_flat_tight_band(cfg):
     assert np.array_equal(np.isfinite(loss), fin)
     assert np.allclose(loss[fin], l64[fin], rtol=1e-4, atol=0)
     for mine, truth, ref32 in ((gm, gm64, gm32), (gl, gl64, gl32)):
-        assert relerr(mine, truth) <= max(1e-4, 1.5 * relerr(ref32, truth)), (relerr(mine, truth), relerr(ref32, truth))
+        assert elem_err(mine, truth) <= grad_tol(ref32, truth), (elem_err(mine, truth), elem_err(ref32, truth))
     # every cell that carries posterior mass must be finite in alpha and beta
     post = a64 + b64 - match.astype(np.float64) - l64[:, None, None]
     relevant = np.isfinite(post) & (post > np.log(1e-12))
@@ -190,7 +222,7 @@ def test_exact_log_domain_switch():
     finally:
         ops.EXACT_LOG_DOMAIN = False
     assert np.allclose(fast[0], exact[0], rtol=1e-5)
-    assert relerr(fast[1], exact[1]) <= 1e-4 and relerr(fast[2], exact[2]) <= 1e-4
+    assert elem_err(fast[1], exact[1]) <= 2e-4 and elem_err(fast[2], exact[2]) <= 2e-4   # two fp32 paths, 1e-4 each
     assert torch.equal(torch.isfinite(fast[3]), torch.isfinite(exact[3]))
     assert torch.equal(torch.isfinite(fast[4]), torch.isfinite(exact[4]))
 
@@ -488,7 +520,7 @@ def test_criterion_style_chain_end_to_end():
     l_c, g1_c, g2_c = chain(True)
     l_t, g1_t, g2_t = chain(False)
     assert abs(l_c - l_t) <= 1e-4 * abs(l_t)
-    assert relerr(g2_c.cpu().numpy(), g2_t.cpu().numpy()) <= 1e-4
+    assert elem_err(g2_c.cpu().numpy(), g2_t.cpu().numpy()) <= 2e-4    # two fp32 paths against each other
     assert relerr(g1_c.cpu().numpy(), g1_t.cpu().numpy()) <= 2e-2  # fp16 logits gradient
 
 
@@ -513,6 +545,41 @@ def test_non_default_stream_and_empty_batch():
     e = ops.dag_loss(torch.zeros(0, 4, 8, device=DEV), torch.zeros(0, 8, 7, device=DEV),
                      torch.zeros(0, dtype=torch.long, device=DEV), torch.zeros(0, dtype=torch.long, device=DEV))
     assert e.shape == (0,)
+
+
+def test_blocked_recurrences_repeatable_back_to_back_on_two_streams():
+    """The tcgen05 recurrences hand data between warps through mailboxes, mbarriers and the async proxy; a missing fence
+    shows up as a rare run-to-run difference.  200 back-to-back launches at the C2 shape, alternating between two
+    streams that run concurrently (each with its own workspace), must reproduce loss, alpha and beta BIT FOR BIT."""
+    B, L, M = 32, 1024, 256
+    T = L - 1
+    g = torch.Generator(device=DEV).manual_seed(77)
+    match = torch.log(torch.rand(B, M, L, device=DEV, generator=g) * 0.98 + 0.01)
+    tl = torch.randint(M // 2, M + 1, (B,), device=DEV, generator=g)
+    ol = torch.maximum(torch.randint(L // 2, L + 1, (B,), device=DEV, generator=g), tl)
+    raw = torch.randn(B, L, T, device=DEV, generator=g)
+    i = torch.arange(L, device=DEV).view(1, L, 1)
+    kk = torch.arange(T, device=DEV).view(1, 1, T)
+    valid = (i + kk + 1) < ol.view(B, 1, 1)
+    links = torch.log_softmax(raw.masked_fill(~valid, float("-inf")), -1).masked_fill(~valid, float("-inf")).contiguous()
+    del raw, valid
+    k = ops.get_dag_kernel()
+    a0, b0 = k.dag_loss(match, links, ol, tl, True, 1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(b0[:, 0, 0]).all()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bad = [torch.zeros((), dtype=torch.int64, device=DEV) for _ in streams]
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream())
+    for it in range(200):
+        si = it & 1
+        with torch.cuda.stream(streams[si]):
+            a, b = k.dag_loss(match, links, ol, tl, True, 1)
+            bad[si] += (a.view(torch.int32) != a0.view(torch.int32)).sum() + (b.view(torch.int32) != b0.view(torch.int32)).sum()
+            del a, b
+    for s in streams:
+        s.synchronize()
+    assert int(bad[0]) == 0 and int(bad[1]) == 0, (int(bad[0]), int(bad[1]))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -549,16 +616,16 @@ def test_against_compiled_reference_cuda_extension(shape):
     check_lattice_side_outputs(a1.cpu().numpy(), b1.cpu().numpy(), a0.double().cpu().numpy(), b0.double().cpu().numpy(),
                                match, z0.double().cpu().numpy())
     # both are fp32 log-domain: judge both against the fp64 truth when the lattice is big
-    scale = 1.0
-    if M * L >= 100000:
-        _, oa, ob = oracle.dag_loss(match, links, olen, tlen, True, np.float64)
-        ogm, ogl = oracle.dag_loss_backward(go.cpu().numpy(), oa, ob, match, links, olen, tlen, np.float64)
-        e_ref = max(relerr(gm0.cpu().numpy(), ogm), relerr(gl0.cpu().numpy(), ogl))
-        e_new = max(relerr(gm1.cpu().numpy(), ogm), relerr(gl1.cpu().numpy(), ogl))
+    # both are fp32 log-domain at the boundary: judge both, element-wise, against the fp64 truth; the new kernels must
+    # be within max(1e-4, 1.5 x the reference CUDA kernels' own error), and within the sum of the two of each other
+    _, oa, ob = oracle.dag_loss(match, links, olen, tlen, True, np.float64)
+    ogm, ogl = oracle.dag_loss_backward(go.cpu().numpy(), oa, ob, match, links, olen, tlen, np.float64)
+    for mine, theirs, truth in ((gm1, gm0, ogm), (gl1, gl0, ogl)):
+        mine, theirs = mine.cpu().numpy(), theirs.cpu().numpy()
+        e_new, e_ref = elem_err(mine, truth), elem_err(theirs, truth)
+        print("elem grad errors vs fp64: new", e_new, "reference CUDA", e_ref)
         assert e_new <= max(1e-4, 1.5 * e_ref), (e_new, e_ref)
-        scale = max(1.0, 2.5 * e_ref / 1e-4)
-    assert relerr(gm1.cpu().numpy(), gm0.cpu().numpy()) <= 1e-4 * scale
-    assert relerr(gl1.cpu().numpy(), gl0.cpu().numpy()) <= 1e-4 * scale
+        assert elem_err(mine, theirs) <= max(1e-4, e_new + e_ref)
     # Viterbi: indices bit-exact against the reference CUDA kernel
     av0, p0 = ref.dag_best_alignment(m, lk, ol, tl, 1)
     av1, p1 = k.dag_best_alignment(m, lk, ol, tl, 1)
@@ -575,6 +642,119 @@ def test_against_compiled_reference_cuda_extension(shape):
     torch.cuda.synchronize()
     assert torch.allclose(s1, s0, rtol=1e-3, atol=1e-4)
     assert torch.allclose(xb.float(), xa.float(), rtol=2e-3, atol=1e-6)
+
+
+def test_pybind_shim_is_a_drop_in_for_the_reference_native_module():
+    """daspeech_b200/csrc/dag_loss_fn.so called exactly as the reference's Python layer calls its native module
+    (custom_ops/dag_loss.py:105,118,227,272 and the two torch ops of :294-295): same results, bit for bit, as the
+    ctypes operator layer on the same tensors."""
+    from daspeech_b200.csrc import build_shim
+    mod = build_shim.load()
+    k = ops.get_dag_kernel()
+    B, L, M, T, V = 3, 200, 30, 199, 1000
+    match, links, olen, tlen = oracle.make_lattice(B, L, M, T, seed=31, ragged=True)
+    m, lk, ol, tl = cu(match), cu(links), cu(olen), cu(tlen)
+    go = torch.rand(B, device=DEV) + 0.5
+    a0, b0 = k.dag_loss(m, lk, ol, tl, True, 1)
+    a1, b1 = mod.dag_loss(m, lk, ol, tl, True, 1)
+    assert torch.equal(a0, a1) and torch.equal(b0, b1)
+    a2, b2 = mod.dag_loss(m, lk, ol, tl, False, 1)
+    assert torch.equal(a2, a0) and not b2.any()
+    gm0, gl0 = k.dag_loss_backward(go, a0, b0, m, lk, ol, tl, 2, 2)
+    gm1, gl1 = mod.dag_loss_backward(go, a1, b1, m, lk, ol, tl, 2, 2)
+    assert torch.equal(gm0, gm1) and torch.equal(gl0, gl1)
+    av0, p0 = k.dag_best_alignment(m, lk, ol, tl, 1)
+    av1, p1 = mod.dag_best_alignment(m, lk, ol, tl, 1)
+    assert p1.dtype == torch.int32 and torch.equal(p0, p1) and torch.equal(av0, av1)
+    # gather + the reference wrapper's own backward ops on the buffer the module overwrote
+    x = (torch.randn(B, L, V, device=DEV) * 2).half()
+    idx = torch.randint(0, V, (B, M), device=DEV).unsqueeze(1).expand(-1, L, -1)
+    xa, xb = x.clone(), x.clone()
+    s0 = k.logsoftmax_gather(xa, idx, True)
+    s1 = mod.logsoftmax_gather(xb, idx, True)
+    assert s1.shape == (B, L, M) and torch.equal(s0, s1) and torch.equal(xa, xb)
+    g = torch.randn(B, L, M, device=DEV)
+    gi = xb.mul_(g.sum(-1, keepdim=True).neg().to(xb.dtype))        # dag_loss.py:294
+    gi.scatter_add_(-1, idx, g.to(xb.dtype))                         # dag_loss.py:295
+    k.logsoftmax_gather_backward(xa, idx, g)
+    assert relerr(xa.float().cpu().numpy(), gi.float().cpu().numpy()) <= 2e-2
+    with pytest.raises(RuntimeError, match="length should be long"):
+        mod.dag_loss(m, lk, ol.int(), tl, True, 1)
+    with pytest.raises(RuntimeError, match="select_idx should be long"):
+        mod.logsoftmax_gather(x.clone(), idx.int(), True)
+
+
+def test_logsoftmax_gather_backward_has_no_vocabulary_limit():
+    """Vocabularies beyond the shared-memory staging limit (> ~51 k fp32 elements) take the global-memory backward: the
+    forward must not succeed on a shape whose backward then fails (the reference's mul_ + scatter_add_ has no limit)."""
+    torch.manual_seed(2)
+    B, L, V, S = 1, 5, 66000, 9
+    for dtype, gtol in ((torch.float32, 1e-4), (torch.float16, 2e-2), (torch.float64, 1e-9)):
+        x0 = (torch.randn(B, L, V, device=DEV) * 2).to(dtype)
+        tg = torch.randint(0, V, (B, S), device=DEV)
+        tg[0, 1] = tg[0, 0]                                           # a duplicate target: the scatter accumulates
+        idx = tg.unsqueeze(1).expand(-1, L, -1)
+        w = torch.randn(B, L, S, device=DEV)
+        xr = x0.double().requires_grad_()
+        sel_ref = torch.log_softmax(xr, -1).gather(-1, idx)
+        gref = torch.autograd.grad((sel_ref * w.double()).sum(), [xr])[0]
+        leaf = x0.clone().requires_grad_()
+        _, sel = ops.dag_logsoftmax_gather_inplace(leaf * 1, idx)
+        assert torch.allclose(sel.double(), sel_ref.detach(), rtol=2e-5, atol=2e-4)
+        grad = torch.autograd.grad((sel * w.to(sel.dtype)).sum(), [leaf])[0]
+        assert relerr(grad.double().cpu().numpy(), gref.cpu().numpy()) <= gtol
+
+
+def test_workspace_contents_never_leak_between_calls():
+    """The cached scratch is uninitialised and reused: poison it with NaN bit patterns, then run a ragged lattice whose
+    tiles beyond each utterance's length are skipped by the precompute -- results must not change."""
+    match, links, olen, tlen = oracle.make_lattice(3, 300, 40, 299, seed=77, ragged=True)
+    go = np.ones(3, np.float32)
+    k = ops.get_dag_kernel()
+    first = run_loss(match, links, olen, tlen, go, torch.float32, True)
+    for buf in list(k._scratch.values()):
+        buf.fill_(0xFF)
+    again = run_loss(match, links, olen, tlen, go, torch.float32, True)
+    assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1]) and np.array_equal(first[2], again[2])
+    assert torch.equal(first[3], again[3]) and torch.equal(first[4], again[4])
+    p0 = ops.dag_best_alignment(cu(match), cu(links), cu(olen), cu(tlen))
+    for buf in list(k._scratch.values()):
+        buf.fill_(0xFF)
+    assert torch.equal(p0, ops.dag_best_alignment(cu(match), cu(links), cu(olen), cu(tlen)))
+    k.release_workspaces()
+    assert not k._scratch
+
+
+def test_sharded_nll_on_cuda_single_process():
+    """daspeech_b200.dist on CUDA tensors (the gloo test covers the two-rank logic on CPU): every logging scalar lives on
+    the loss device, so the flat stats tensor can be all-reduced over NCCL."""
+    from daspeech_b200 import dist as ddist
+    match, links, olen, tlen = oracle.make_lattice(4, 40, 9, 39, seed=3, ragged=True)
+    mean, local, stats = ddist.dag_nll_sharded(ops.dag_loss, cu(match), cu(links), cu(olen), cu(tlen))
+    assert all(v.is_cuda for v in stats.values())
+    l64, _, _ = oracle.dag_loss(match, links, olen, tlen, False, np.float64)
+    assert abs(float(mean) - float(-(l64 / tlen).mean())) <= 1e-4 * abs(float(mean))
+    assert int(stats["nsentences"]) == 4 and int(stats["ntokens"]) == int(tlen.sum())
+    ex = ddist.FlatGradAllReduce(1 << 16, torch.float32, torch.device(DEV))
+    ex.buffer.fill_(2.0)
+    ex.start()
+    assert float(ex.finish().sum()) == 2.0 * (1 << 16)     # world size 1: unchanged
+
+
+def test_device_status_is_reported_without_debug_mode():
+    """Per-sample precondition violations (the reference's CUDA_KERNEL_ASSERTs) are always recorded; outside
+    DAGB200_DEBUG they surface as a RuntimeWarning at the next status check instead of a sticky device assert."""
+    import warnings
+    match, links, olen, tlen = oracle.make_lattice(2, 20, 6, 19, seed=3, ragged=False)
+    tlen[1] = 1                                                      # target length < 2 (dag_loss.cu:68)
+    k = ops.get_dag_kernel()
+    k.check_pending_status(wait=True)
+    a, b = k.dag_loss(cu(match), cu(links), cu(olen), cu(tlen), True, 1)
+    assert torch.isinf(b[1]).all() and torch.isfinite(b[0, 0, 0])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        k.check_pending_status(wait=True)
+    assert any("at least 2" in str(x.message) for x in w)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -634,6 +814,7 @@ def test_full_size_c2_properties():
     gm32, gl32 = oracle.dag_loss_backward(gg, a32, b32, mm, ll, oo, tt, np.float32)
     assert np.allclose(loss[sub].detach().cpu().numpy(), l64, rtol=1e-4, atol=0)
     for mine, truth, ref32 in ((gm[sub].cpu().numpy(), gm64, gm32), (gl[sub].cpu().numpy(), gl64, gl32)):
-        assert relerr(mine, truth) <= max(1e-4, 1.5 * relerr(ref32, truth)), (relerr(mine, truth), relerr(ref32, truth))
+        print("C2 elem grad error", elem_err(mine, truth), "fp32 reference arithmetic", elem_err(ref32, truth))
+        assert elem_err(mine, truth) <= grad_tol(ref32, truth), (elem_err(mine, truth), elem_err(ref32, truth))
     _, opath, _ = oracle.dag_best_alignment(mm, ll, oo, tt, 1, np.float32)
     assert np.array_equal(path[sub].cpu().numpy(), opath.astype(np.int64))
