@@ -1,4 +1,4 @@
-"""Build dag_loss_fn.so (in-tree): the pybind module with the reference's four native entry points
+"""Build dag_loss_fn_b200.so (in-tree): the pybind module with the reference's four native entry points
 (DASpeech/custom_ops/dag_loss.cpp:19-29) on top of libdagb200.so.  Plain g++; called by __graft_entry__.build()."""
 import os
 import subprocess
@@ -7,7 +7,7 @@ import sysconfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "dag_loss_fn_shim.cpp")
-OUT = os.path.join(HERE, "dag_loss_fn.so")
+OUT = os.path.join(HERE, "dag_loss_fn_b200.so")
 
 
 def build(force=False):
@@ -21,7 +21,7 @@ def build(force=False):
     from torch.utils import cpp_extension as ce
     inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
     libdirs = ce.library_paths()
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", SRC, "-o", OUT, "-DTORCH_EXTENSION_NAME=dag_loss_fn",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", SRC, "-o", OUT, "-DTORCH_EXTENSION_NAME=dag_loss_fn_b200",
            "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
     cmd += ["-I" + i for i in inc]
     cmd += ["-L" + d for d in libdirs] + ["-L" + HERE]
@@ -40,7 +40,7 @@ def load():
     import torch  # noqa: F401
     if not os.path.exists(OUT):
         raise RuntimeError("%s is missing: run daspeech_b200/csrc/build_shim.py" % OUT)
-    spec = importlib.util.spec_from_file_location("dag_loss_fn", OUT)
+    spec = importlib.util.spec_from_file_location("dag_loss_fn_b200", OUT)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod

@@ -416,18 +416,20 @@ extern "C" int dagb200_dag_loss(const void *match, const void *links, const int6
 }
 
 namespace dagb200 {
-bool vit2_supported(int M, int L);
-int launch_viterbi_blocked(const float *match, const float *links, const int64_t *olen, const int64_t *tlen,
-                           float *lattice, uint16_t *trace, int32_t *path, unsigned char *flags, int B, int M, int L,
-                           int Tl, int32_t *status, cudaStream_t st);
+size_t vit3_hand_bytes(int B, int L);
+int launch_viterbi_wave(const float *match, const float *links, const int64_t *olen, const int64_t *tlen, float *lattice,
+                        int32_t *path, float *hand_g, int full_lattice, int B, int M, int L, int Tl, int32_t *status,
+                        cudaStream_t st);
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace dagb200
 
-// trace (uint16 per cell) + a lattice plane for the case the caller does not want alpha back
+// workspace: [trace, uint16 per cell (exact kernels)] [lattice plane, for callers that do not want alpha back]
+//            [hand-down rows of the wave kernel]
 extern "C" size_t dagb200_best_alignment_workspace_bytes(int B, int M, int L, int T) {
   (void)T;
+  if (B <= 0 || M < 1 || L < 1) return 0;
   const size_t cells = (size_t)B * M * L;
-  const size_t flags = ((size_t)B * M * ((L + 31) / 32) + 255) & ~(size_t)255;   // per (row, 32-vertex block) flags
-  return ((cells * sizeof(uint16_t) + 255) & ~(size_t)255) + ((cells * sizeof(float) + 255) & ~(size_t)255) + flags;
+  return align256(cells * sizeof(uint16_t)) + align256(cells * sizeof(float)) + vit3_hand_bytes(B, L);
 }
 
 extern "C" int dagb200_dag_best_alignment(const void *match, const void *links, const int64_t *output_length,
@@ -443,14 +445,15 @@ extern "C" int dagb200_dag_best_alignment(const void *match, const void *links, 
                     DAGB200_EWORKSPACE, "dag_best_alignment: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int wbits = config + 1;  // config 1..4 -> TRANS_BLOCK_SIZE 4/8/16/32 (dag_best_alignment.cu:243-246)
-  if (dtype == DAGB200_F32 && config == 1 && !g_exact_mode && vit2_supported(M, L)) {
-    const size_t cells = (size_t)B * M * L;
-    float *lattice = alpha ? (float *)alpha
-                           : reinterpret_cast<float *>((unsigned char *)workspace + ((cells * sizeof(uint16_t) + 255) & ~(size_t)255));
-    unsigned char *flags = (unsigned char *)workspace + ((cells * sizeof(uint16_t) + 255) & ~(size_t)255) +
-                           ((cells * sizeof(float) + 255) & ~(size_t)255);
-    return launch_viterbi_blocked((const float *)match, (const float *)links, output_length, target_length, lattice,
-                                  (uint16_t *)workspace, path, flags, B, M, L, T, status, st);
+  const size_t cells = (size_t)B * M * L;
+  unsigned char *ws = (unsigned char *)workspace;
+  if (dtype == DAGB200_F32 && config == 1 && !g_exact_mode && 2 * (int64_t)B <= 2147483647) {
+    // wave-pipelined blocked kernel (dag_viterbi3.cu); without an alpha output only the cells that can reach the end
+    // cell are computed, in a scratch lattice
+    float *lattice = alpha ? (float *)alpha : reinterpret_cast<float *>(ws + align256(cells * sizeof(uint16_t)));
+    float *hand = reinterpret_cast<float *>(ws + align256(cells * sizeof(uint16_t)) + align256(cells * sizeof(float)));
+    return launch_viterbi_wave((const float *)match, (const float *)links, output_length, target_length, lattice, path,
+                               hand, alpha ? 1 : 0, B, M, L, T, status, st);
   }
   if (dtype == DAGB200_F32)
     return launch_viterbi<float>((const float *)match, (const float *)links, output_length, target_length,

@@ -1,4 +1,6 @@
-// dag_loss_fn_shim.cpp -- pybind module `dag_loss_fn`: the reference's native boundary on top of libdagb200.so.
+// dag_loss_fn_shim.cpp -- pybind module `dag_loss_fn_b200`: the reference's native boundary (its module `dag_loss_fn`) on top
+// of libdagb200.so.  (A distinct module name: pybind11 caches extension modules by name, so two modules called
+// `dag_loss_fn` cannot coexist in one process -- the differential tests load the reference's next to this one.)
 //
 // The reference binds four torch::Tensor functions in DASpeech/custom_ops/dag_loss.cpp:19-29 and its Python layer calls
 // them through get_dag_kernel() (custom_ops/dag_loss.py:37-64, 105, 118, 169, 182, 227, 272).  This file exports the
@@ -68,8 +70,12 @@ void check_lattice(const torch::Tensor &match_all, const torch::Tensor &links, c
 
 }  // namespace
 
+// The four entry points live in their own namespace with internal linkage: the reference's extension exports global
+// functions with the same names and signatures (dag_loss.cpp:19-22), and both modules may be loaded in one process.
+namespace dagb200_shim {
+
 // dag_loss.cpp:19 / dag_loss.cu:313-375
-std::tuple<torch::Tensor, torch::Tensor> dag_loss(const torch::Tensor &match_all_, const torch::Tensor &links_,
+static std::tuple<torch::Tensor, torch::Tensor> dag_loss(const torch::Tensor &match_all_, const torch::Tensor &links_,
                                                   const torch::Tensor &output_length_, const torch::Tensor &target_length_,
                                                   bool require_gradient, int config) {
   check_lattice(match_all_, links_, output_length_, target_length_);
@@ -89,7 +95,7 @@ std::tuple<torch::Tensor, torch::Tensor> dag_loss(const torch::Tensor &match_all
 }
 
 // dag_loss.cpp:20 / dag_loss.cu:518-571
-std::tuple<torch::Tensor, torch::Tensor> dag_loss_backward(const torch::Tensor &grad_output_, const torch::Tensor &alpha_,
+static std::tuple<torch::Tensor, torch::Tensor> dag_loss_backward(const torch::Tensor &grad_output_, const torch::Tensor &alpha_,
                                                            const torch::Tensor &beta_, const torch::Tensor &match_all_,
                                                            const torch::Tensor &links_, const torch::Tensor &output_length_,
                                                            const torch::Tensor &target_length_, int config1, int config2) {
@@ -112,7 +118,7 @@ std::tuple<torch::Tensor, torch::Tensor> dag_loss_backward(const torch::Tensor &
 }
 
 // dag_loss.cpp:21 / dag_best_alignment.cu:209-253: returns (max-plus lattice, path int32 [B, L])
-std::tuple<torch::Tensor, torch::Tensor> dag_best_alignment(const torch::Tensor &match_all_, const torch::Tensor &links_,
+static std::tuple<torch::Tensor, torch::Tensor> dag_best_alignment(const torch::Tensor &match_all_, const torch::Tensor &links_,
                                                             const torch::Tensor &output_length_,
                                                             const torch::Tensor &target_length_, int config) {
   check_lattice(match_all_, links_, output_length_, target_length_);
@@ -133,7 +139,7 @@ std::tuple<torch::Tensor, torch::Tensor> dag_best_alignment(const torch::Tensor 
 }
 
 // dag_loss.cpp:22 / logsoftmax_gather.cu:313-377: word_ins_out is overwritten with probabilities iff require_gradient
-torch::Tensor logsoftmax_gather(torch::Tensor word_ins_out, const torch::Tensor &select_idx, bool require_gradient) {
+static torch::Tensor logsoftmax_gather(torch::Tensor word_ins_out, const torch::Tensor &select_idx, bool require_gradient) {
   TORCH_CHECK(word_ins_out.is_cuda() && select_idx.is_cuda(), "inputs must be CUDA tensors");
   TORCH_CHECK(word_ins_out.dim() == 3, "word_ins_out dim != 3");
   TORCH_CHECK(select_idx.dim() == 3, "select_idx dim != 3");
@@ -156,9 +162,12 @@ torch::Tensor logsoftmax_gather(torch::Tensor word_ins_out, const torch::Tensor 
   return result;
 }
 
+}  // namespace dagb200_shim
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-  m.def("dag_loss", &dag_loss, "alpha / beta lattices of the DAG log-marginal (libdagb200)");
-  m.def("dag_loss_backward", &dag_loss_backward, "emission and transition gradients (libdagb200)");
-  m.def("dag_best_alignment", &dag_best_alignment, "Viterbi lattice and alignment path (libdagb200)");
-  m.def("logsoftmax_gather", &logsoftmax_gather, "fused vocabulary log-softmax + target gather (libdagb200)");
+  using namespace dagb200_shim;
+  m.def("dag_loss", &dagb200_shim::dag_loss, "alpha / beta lattices of the DAG log-marginal (libdagb200)");
+  m.def("dag_loss_backward", &dagb200_shim::dag_loss_backward, "emission and transition gradients (libdagb200)");
+  m.def("dag_best_alignment", &dagb200_shim::dag_best_alignment, "Viterbi lattice and alignment path (libdagb200)");
+  m.def("logsoftmax_gather", &dagb200_shim::logsoftmax_gather, "fused vocabulary log-softmax + target gather (libdagb200)");
 }

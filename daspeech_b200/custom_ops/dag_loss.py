@@ -79,6 +79,8 @@ class _DagKernel:
         self.lib = _lib.load()
         self._scratch = {}
         self._pending = []      # (what, pinned host copy of the per-sample status, event) of earlier calls
+        self._pinned = None
+        self._pin_next = 0
 
     # ---- per-sample device status (the reference's CUDA_KERNEL_ASSERTs, dag_loss.cu:68-69, dag_best_alignment.cu:67-70,118)
     # The status words are always produced (B int32).  DAGB200_DEBUG=1 checks them synchronously and raises; otherwise
@@ -88,7 +90,16 @@ class _DagKernel:
         if _DEBUG:
             _check_status(status)
             return
-        host = torch.empty(status.shape, dtype=status.dtype, pin_memory=True)
+        # a small ring of persistent pinned buffers: no host allocation on the launch path
+        n = status.numel()
+        if len(self._pending) >= 16:
+            self.check_pending_status(wait=True)
+        if self._pinned is None or self._pinned.shape[1] < n:
+            self.check_pending_status(wait=True)
+            self._pinned = torch.empty((17, max(n, 256)), dtype=torch.int32, pin_memory=True)
+            self._pin_next = 0
+        host = self._pinned[self._pin_next, :n]
+        self._pin_next = (self._pin_next + 1) % self._pinned.shape[0]
         host.copy_(status, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()

@@ -72,7 +72,7 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 
 def test_pybind_shim_exports_the_reference_entry_points():
-    """daspeech_b200/csrc/dag_loss_fn.so: the module a maintainer returns from get_dag_kernel() (INTEGRATION.md option B)
+    """daspeech_b200/csrc/dag_loss_fn_b200.so: the module a maintainer returns from get_dag_kernel() (INTEGRATION.md option B)
     must expose exactly the four callables of DASpeech/custom_ops/dag_loss.cpp:24-29 (import only; no GPU here)."""
     from daspeech_b200.csrc import build_shim
     build_shim.build()

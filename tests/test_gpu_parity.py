@@ -645,7 +645,7 @@ def test_against_compiled_reference_cuda_extension(shape):
 
 
 def test_pybind_shim_is_a_drop_in_for_the_reference_native_module():
-    """daspeech_b200/csrc/dag_loss_fn.so called exactly as the reference's Python layer calls its native module
+    """daspeech_b200/csrc/dag_loss_fn_b200.so called exactly as the reference's Python layer calls its native module
     (custom_ops/dag_loss.py:105,118,227,272 and the two torch ops of :294-295): same results, bit for bit, as the
     ctypes operator layer on the same tensors."""
     from daspeech_b200.csrc import build_shim
