@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdagb200.so")
+# DAGB200_LIB: an alternative build of the same library (instrumented / A-B variants), never a fallback
+LIB_PATH = os.environ.get("DAGB200_LIB") or os.path.join(_HERE, "csrc", "libdagb200.so")
 
 _lock = threading.Lock()
 _lib = None
@@ -42,6 +43,7 @@ SIGNATURES = {
                                             _int, _int, _int, _int, _int, _int, _vp, _sz, _vp]),
     "dagb200_dag_posterior": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "dagb200_glat_force_emit": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "dagb200_glat_alignment": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
     "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "dagb200_dag_best_alignment": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int,
                                           _vp, _sz, _vp, _vp]),

@@ -8,21 +8,29 @@
 // path only.
 //
 // Organisation.  Vertices in blocks of 32, target rows in chunks of 32, tile = (chunk c, block J).  A pass covers 8
-// chunks (256 rows); the chunks of a pass are split by parity between the TWO CTAs of a thread-block cluster (one
-// cluster per utterance).  Tiles are processed in anti-diagonal steps (step = J + local chunk), ONE cluster barrier per
-// step.  Inside a step two kinds of warps run concurrently:
-//   * chain warps (4 per CTA, one per chunk, lanes = rows): the tile of the CURRENT step.  For column cj the lane takes
-//     max(far sums, what the row above hands down) + emission, then computes what its own row hands to the row below:
-//     the max over the 32 sources of the PREVIOUS block (its own values of the step before, still in registers) and the
-//     already finished columns of this block.  The last row's hand-down goes to the chunk below through global memory.
-//   * far warps (12 per CTA, lanes = destination columns): the far-predecessor maxima of the NEXT step's tiles -- all
-//     source blocks up to J-2, which were finished at least one step earlier, so nothing inside a step depends on the
-//     chain warps.  A unit = (tile, source block): the transition column of the lane's vertex lives in 32 registers, the
-//     32x32 tile of previous-row values is staged by cp.async (double-buffered), 32 running maxima stay in registers
-//     across the units of a tile and meet the other warps' maxima in shared memory (integer atomicMax on
-//     order-preserving keys) once per tile.  Units are dealt in contiguous ranges, the same number to every far warp.
+// chunks (256 rows); the chunks of a pass are split {0,3,4,7} / {1,2,5,6} between the TWO CTAs of a thread-block
+// cluster (one cluster per utterance; both CTAs then own the same number of far units in every step).  Tiles are
+// processed in anti-diagonal steps (step = J + local chunk), ONE cluster barrier per step.  Per CTA and step:
+//   * a team of four warps per tile (the chain warp + three helpers) first adds the PREVIOUS block J-1 -- the rows the
+//     chain warp produced one step earlier, kept in shared memory, plus the last row of the chunk above -- to the far
+//     maxima, eight rows per warp, exactly like a far unit (lanes = destination columns).  One named barrier later
+//     the chain warp (lanes = rows) sweeps the 32 columns of the diagonal block in push form: cell = max(far maxima,
+//     what the row above hands down) + emission, then the cell pushes into what its own row hands to the row below for
+//     the later columns -- one add and one max on the column-to-column dependency path.  The last row's hand-down goes
+//     to the chunk below through global memory.  Meanwhile one helper stages the operands of the team's next tile
+//     (double-buffered), so no load latency sits at the head of a step.
+//   * all sixteen warps then pull far units from a shared-memory queue: the far-predecessor maxima of the NEXT step's
+//     tiles from source blocks up to J-2, which were finished at least one step earlier -- nothing inside a step depends
+//     on the chain warps.  A unit = (tile, half a source block): the transition column of the lane's vertex lives in 16
+//     registers, the 32 x 16 tile of previous-row values is staged by cp.async (double-buffered) and read as broadcast
+//     float4s one row ahead of the arithmetic, 32 running maxima stay in registers across the units of a tile and meet
+//     the other warps' maxima in shared memory (integer atomicMax on order-preserving keys) once per tile.
+// Cost model (tools/ubench3.cu, ubench4.cu on B200): one candidate = one FADD + half an FMNMX3, and FMNMX3 issues at
+// half rate, i.e. 2 issue slots per edge whatever the idiom (float or integer min/max); a broadcast LDS.128 issues at
+// most once per ~15 cycles per warp.  The kernel is issue-bound, not HBM-bound: DESIGN.md section 4.6.
 // When the caller does not ask for the lattice (the Python wrapper never does, dag_loss.py:227-230) only cells that can
 // still reach the end cell are computed: column j of row t is skipped when O-1-j < Tn-1-t.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,12 +38,19 @@
 namespace dagb200 {
 namespace v3 {
 
+#ifdef DAGB200_V3_TIMING
+__device__ long long g_v3t[64][8];   // per step: [0] chain busy, [1] far busy (warp 4), [2] step length (warp 4), [3] units of warp 4, [4] far busy warp 15
+#endif
+
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChain = 4;                 // chain warps per CTA = chunks of a pass owned by a CTA
-constexpr int kFar = kWarps - kChain;     // far warps per CTA
+constexpr int kHelp = 3;                  // helper warps per tile team
+constexpr int kHalf = 16;                 // source vertices per far unit
 constexpr int kB = 32;                    // block / chunk edge
 constexpr int kPitch = 33;
+constexpr int kEdPitch = 36;               // 16-byte aligned rows, 4 banks apart
+constexpr int kIoPitch = 36;
 constexpr int kPassChunks = 2 * kChain;   // chunks per pass (both CTAs)
 
 __device__ __forceinline__ int f2key(float x) { const int b = __float_as_int(x); return b ^ ((b >> 31) & 0x7fffffff); }
@@ -53,6 +68,10 @@ __device__ __forceinline__ void cp_async16_cg(float *smem_dst, const float *gsrc
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+
+// local chunk of tile slot ts in CTA `rank`: {0,3,4,7} / {1,2,5,6} -- both CTAs own the same number of far units in
+// every step (a tile of local chunk lc has step - 2 lc - 1 of them)
+__device__ __forceinline__ int chunk_of(int ts, int rank) { return 2 * ts + ((ts ^ rank) & 1); }
 
 __device__ __forceinline__ int rank4(int delta) {  // priority of the class of `delta`: classes 0,2,1,3 -> 0,1,2,3
   const int cl = (delta - 1) & 3;
@@ -80,79 +99,90 @@ struct Geo {
   __device__ __forceinline__ int ilo(int c, int J) const { return max(c, J - band); }
 };
 
-// ---- chain warp: one column of the tile (lanes = rows); everything indexed by compile-time CJ -------------------------
+// ---- chain warp, column sweep (lanes = rows), push formulation: hd[k] = what my row hands to the row below for column
+// k from the columns finished so far; the cell of column CJ pushes into hd[CJ+1 ..].  The only operations on the
+// column-to-column dependency path are one add + one max (hd[CJ+1]), the shuffle, one max and one add.
 template <int CJ>
-__device__ __forceinline__ void chain_column(float (&vrow)[kB], const float (&vprev)[kB], const float *ed, const float *ep,
-                                             const float *iow, const int *xkw, const float *handin, float *handout,
-                                             int lane, bool rowvalid, int jbase, int t, int O, int jmax, bool prev_on) {
+__device__ __forceinline__ void chain_column(float (&hd)[kB], const float *ed, float *iow, const float (&mm)[8],
+                                             const float (&fx)[8], const float (&hin)[8], const float (&e1)[8],
+                                             float *handout, int lane, uint32_t vmask) {
   const float ninf = neg_inf_f();
-  // what the row above hands down for this column; mine is computed below and travels one lane down
-  float n0 = ninf, n1 = ninf;
-  if (prev_on) {
-#pragma unroll
-    for (int c4 = 0; c4 < kB; c4 += 4) {
-      const float4 e4 = *reinterpret_cast<const float4 *>(ep + CJ * kB + c4);
-      n0 = max3(n0, vprev[c4 + 0] + e4.x, vprev[c4 + 1] + e4.y);
-      n1 = max3(n1, vprev[c4 + 2] + e4.z, vprev[c4 + 3] + e4.w);
-    }
-  }
-#pragma unroll
-  for (int c4 = 0; c4 < CJ; c4 += 4) {
-    const float4 e4 = *reinterpret_cast<const float4 *>(ed + CJ * kB + c4);
-    if (c4 + 0 < CJ) n0 = fmaxf(n0, vrow[c4 + 0] + e4.x);
-    if (c4 + 1 < CJ) n1 = fmaxf(n1, vrow[c4 + 1] + e4.y);
-    if (c4 + 2 < CJ) n0 = fmaxf(n0, vrow[c4 + 2] + e4.z);
-    if (c4 + 3 < CJ) n1 = fmaxf(n1, vrow[c4 + 3] + e4.w);
-  }
-  const float n = fmaxf(n0, n1);
+  const float n = hd[CJ];
   float rv = __shfl_up_sync(0xffffffffu, n, 1);
-  if (lane == 0) rv = handin[CJ];
+  if (lane == 0) rv = hin[CJ & 7];
   if (lane == kB - 1) handout[CJ] = n;
-  const float best = fmaxf(rv, key2f(xkw[CJ]));
-  const int j = jbase + CJ;
-  const bool valid = rowvalid && j >= t && j < O && j <= jmax;
-  vrow[CJ] = valid ? best + iow[CJ] : ninf;
+  const float best = fmaxf(rv, fx[CJ & 7]);
+  const float v = ((vmask >> CJ) & 1u) ? best + mm[CJ & 7] : ninf;
+  if (CJ + 1 < kB) hd[(CJ + 1) & (kB - 1)] = fmaxf(hd[(CJ + 1) & (kB - 1)], v + e1[CJ & 7]);   // the next column first
+  iow[CJ] = v;
+  // push into the later columns: ed[CJ][k] = transition from vertex CJ of this block to vertex k (source-major tile)
+#pragma unroll
+  for (int k4 = (CJ + 2) & ~3; k4 < kB; k4 += 4) {
+    const float4 e4 = *reinterpret_cast<const float4 *>(ed + CJ * kEdPitch + k4);
+    if (k4 + 0 > CJ + 1) hd[k4 + 0] = fmaxf(hd[k4 + 0], v + e4.x);
+    if (k4 + 1 > CJ + 1) hd[k4 + 1] = fmaxf(hd[k4 + 1], v + e4.y);
+    if (k4 + 2 > CJ + 1) hd[k4 + 2] = fmaxf(hd[k4 + 2], v + e4.z);
+    if (k4 + 3 > CJ + 1) hd[k4 + 3] = fmaxf(hd[k4 + 3], v + e4.w);
+  }
 }
+// eight columns: their emissions, far maxima, hand-ins and next-column transitions are fetched before the first needs them
 template <int CJ0>
-__device__ __forceinline__ void chain_group(float (&vrow)[kB], const float (&vprev)[kB], const float *ed, const float *ep,
-                                            const float *iow, const int *xkw, const float *handin, float *handout, int lane,
-                                            bool rowvalid, int jbase, int t, int O, int jmax, bool prev_on) {
-  chain_column<CJ0 + 0>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 1>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 2>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 3>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 4>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 5>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 6>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
-  chain_column<CJ0 + 7>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, jbase, t, O, jmax, prev_on);
+__device__ __forceinline__ void chain_group(float (&hd)[kB], const float *ed, float *iow, const int *xkw,
+                                            const float *handin, float *handout, int lane, uint32_t vmask) {
+  float mm[8], fx[8], hin[8], e1[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    mm[k] = iow[CJ0 + k];
+    fx[k] = key2f(xkw[CJ0 + k]);
+    hin[k] = handin[CJ0 + k];
+    e1[k] = (CJ0 + k + 1 < kB) ? ed[(CJ0 + k) * kEdPitch + ((CJ0 + k + 1) & (kB - 1))] : neg_inf_f();
+  }
+  chain_column<CJ0 + 0>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 1>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 2>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 3>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 4>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 5>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 6>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
+  chain_column<CJ0 + 7>(hd, ed, iow, mm, fx, hin, e1, handout, lane, vmask);
 }
 
-// stage the operands of the chain tile (c, J): diagonal block [cj][ci], previous-block transitions [cj][ci] (source
-// block J-1), emissions [row][cj]; lanes = destination columns, 4-byte asynchronous copies (any Tl / alignment)
+// stage the operands of the chain tile (c, J) asynchronously.  Diagonal block, source-major [ci][cj]: row ci holds the
+// first 31 - ci transitions of links row 32 J + ci (one coalesced, conflict-free 4-byte copy per row and lane); emissions
+// [row][cj]: 16-byte copies when the lattice rows are 16-byte aligned.
 __device__ __forceinline__ void chain_stage(const Geo &g, const float *__restrict__ m, const float *__restrict__ E, float *ed,
-                                            float *ep, float *io, int c, int J, int lane) {
+                                            float *io, int c, int J, int lane, bool vec_m) {
   const float ninf = neg_inf_f();
   const int j = kB * J + lane;
   const bool jok = j < g.O;
-#pragma unroll 4
+  const float *erow = E + (int64_t)(kB * J) * g.Tl - 1;      // erow[ci * (Tl - 1) + lane] = E[32 J + ci][lane - ci - 1]
+#pragma unroll 8
   for (int rr = 0; rr < kB; rr++) {
-    {   // diagonal block: source vertex 32J + rr, destination j
-      const int i = kB * J + rr, k = lane - rr - 1;
-      if (k >= 0 && k < g.Tl && jok) cp_async4(ed + lane * kB + rr, E + (int64_t)i * g.Tl + k);   // i < j < O
-      else ed[lane * kB + rr] = ninf;
+    const int k = lane - rr - 1;
+    if (k >= 0 && k < g.Tl && jok) cp_async4(ed + rr * kEdPitch + lane, erow + (int64_t)rr * (g.Tl - 1) + lane);   // 32 J + rr < j < O
+    else ed[rr * kEdPitch + lane] = ninf;
+  }
+  const int s0 = c * kB;
+  if (vec_m && kB * J + kB <= g.L) {
+    const int q = lane & 7;
+#pragma unroll
+    for (int rr = lane >> 3; rr < kB; rr += 4) {
+      float *dst = io + rr * kIoPitch + 4 * q;
+      if (s0 + rr < g.nsteps) cp_async16_cg(dst, m + (int64_t)(1 + s0 + rr) * g.L + kB * J + 4 * q);
+      else *reinterpret_cast<float4 *>(dst) = make_float4(ninf, ninf, ninf, ninf);
     }
-    {   // previous block: source vertex 32(J-1) + rr
-      const int i = kB * (J - 1) + rr, k = kB + lane - rr - 1;
-      if (J > 0 && k < g.Tl && jok) cp_async4(ep + lane * kB + rr, E + (int64_t)i * g.Tl + k);
-      else ep[lane * kB + rr] = ninf;
-    }
-    {   // emissions of row t = 32c + 1 + rr
-      const int s = c * kB + rr;
-      if (s < g.nsteps && j < g.L) cp_async4(io + rr * kPitch + lane, m + (int64_t)(1 + s) * g.L + j);
-      else io[rr * kPitch + lane] = ninf;
+  } else {
+#pragma unroll 8
+    for (int rr = 0; rr < kB; rr++) {
+      if (s0 + rr < g.nsteps && j < g.L) cp_async4(io + rr * kIoPitch + lane, m + (int64_t)(1 + s0 + rr) * g.L + j);
+      else io[rr * kIoPitch + lane] = ninf;
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void team_sync(int ts) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + ts), "r"(32 * (1 + kHelp)) : "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -161,6 +191,9 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
                         int32_t *__restrict__ path, float *hand_g, int M, int L, int Tl, int NB, int full_lattice,
                         int32_t *__restrict__ status) {
   extern __shared__ __align__(16) unsigned char v3_smem[];
+#ifdef DAGB200_V3_TIMING
+  const long long tkernel0 = clock64();
+#endif
   const int b = blockIdx.x >> 1, rank = blockIdx.x & 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int O = (int)olen[b], Tn = (int)tlen[b];
@@ -197,20 +230,23 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
   const int NP = (g.NCv + kPassChunks - 1) / kPassChunks;
 
   // shared memory
-  float *s_ed, *s_ep, *s_io, *s_hand, *s_vs;
-  int *s_xk;
+  float *s_ed, *s_pv, *s_io, *s_hand, *s_vs;
+  int *s_xk, *s_queue;
   {
     float *p = reinterpret_cast<float *>(v3_smem);
-    s_ed = p;   p += kChain * kB * kB;                 // [tile][cj][ci]
-    s_ep = p;   p += kChain * kB * kB;                 // [tile][cj][ci]
-    s_io = p;   p += kChain * kB * kPitch;             // [tile][row][cj] emissions in, cell values out
+    s_ed = p;   p += 2 * kChain * kB * kEdPitch;       // [block parity][tile][ci][cj] diagonal transition block (source-major)
+    s_io = p;   p += 2 * kChain * kB * kIoPitch;       // [block parity][tile][row][cj] emissions in, cell values out
+    s_pv = p;   p += kChain * kB * kEdPitch;           // [tile][source row][ci] values of the previous block: row 0 = last row of
+                                                       // the chunk above, rows 1..31 = my rows 0..30
     s_xk = reinterpret_cast<int *>(p);  p += 2 * kChain * kB * kPitch;   // [step parity][tile][row][cj] far maxima (keys)
     s_hand = p; p += kChain * 2 * kB;                  // [tile][in | out][cj]
-    s_vs = p;                                          // [far warp][2][32][32] previous-row values of a unit
+    s_queue = reinterpret_cast<int *>(p);  p += 4;     // [step parity] next far unit
+    s_vs = p;                                          // [warp][2][32 rows][16 sources] previous-row values of a unit
   }
 
   // ---- prologue (split between the two CTAs) ----------------------------------------------------------------
   for (int x = threadIdx.x; x < 2 * kChain * kB * kPitch; x += kThreads) s_xk[x] = f2key(ninf);
+  if (threadIdx.x < 4) s_queue[threadIdx.x] = 0;
   if (g.full) {
     // everything outside the computed tiles is -inf; the tiles overwrite their part after the barrier below
     const int64_t half = (latsz + 1) / 2;
@@ -228,160 +264,257 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
   }
   cluster_sync_all();
 
-  const bool is_chain = warp < kChain;
-  const int fw = warp - kChain;                       // far warp index
-  float *vs0 = s_vs + (size_t)(fw < 0 ? 0 : fw) * 2 * kB * kB;
+  // team of a tile slot: the chain warp (sub 0) and three helpers (sub 1..3)
+  const int ts = warp < kChain ? warp : (warp - kChain) / kHelp;
+  const int sub = warp < kChain ? 0 : (warp - kChain) % kHelp + 1;
+  const int lc = chunk_of(ts, rank);
+  float *vs0 = s_vs + (size_t)warp * 2 * kB * kHalf;
   const bool vec_ok = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(lat) & 15) == 0);
+  const bool vec_m = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(m) & 15) == 0);
+  float *pv = s_pv + ts * kB * kEdPitch;
+  float *handin = s_hand + ts * 2 * kB, *handout = handin + kB;
 
   for (int p = 0; p < NP; p++) {
     const int cpass = min(kPassChunks, g.NCv - kPassChunks * p);    // chunks of this pass
     const int nst = g.NBv + cpass - 1;                               // anti-diagonal steps
-    float vprev[kB];
-#pragma unroll
-    for (int k = 0; k < kB; k++) vprev[k] = ninf;
-    bool staged = false;
+    const int c = kPassChunks * p + lc;
     // tiles of this pass need J >= c >= 8p: the steps before 8p - 1 are empty
     for (int sg = kPassChunks * p - 1; sg < nst; sg++) {
-      if (is_chain) {
-        // ======================= chain warp: tile (c, J = sg - lc) of this step ==================================
-        const int ts = warp, lc = 2 * ts + rank, c = kPassChunks * p + lc;
-        const int J = sg - lc;
-        float *ed = s_ed + ts * kB * kB, *ep = s_ep + ts * kB * kB, *io = s_io + ts * kB * kPitch;
-        float *handin = s_hand + ts * 2 * kB, *handout = handin + kB;
+#ifdef DAGB200_V3_TIMING
+      const long long tstep0 = clock64();
+      const bool tlog = blockIdx.x == 0 && lane == 0 && sg >= 0 && sg < 64;
+#endif
+      const int J = sg - lc;
+      if (sg >= 0 && lc < cpass && g.tile_alive(c, J)) {
+        // ======================= the team's tile (c, J) of this step ================================================
+        float *ed = s_ed + ((J & 1) * kChain + ts) * kB * kEdPitch, *io = s_io + ((J & 1) * kChain + ts) * kB * kIoPitch;
         int *xk = s_xk + ((sg & 1) * kChain + ts) * kB * kPitch;
-        if (sg >= 0 && lc < cpass && g.tile_alive(c, J)) {
-          if (!staged) chain_stage(g, m, E, ed, ep, io, c, J, lane);
-          handin[lane] = __ldcg(HG + (size_t)lc * NB * kB + kB * J + lane);     // posted by the chunk above, an earlier step
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          __syncwarp();
+        if (sub == 1 && J == c) chain_stage(g, m, E, ed, io, c, J, lane, vec_m);       // first tile of the chunk: nothing staged yet
+        if (sub == 0) handin[lane] = __ldcg(HG + (size_t)lc * NB * kB + kB * J + lane);  // posted by the chunk above, an earlier step
+        if (J > c) {
+          // ---- phase A (lanes = destination columns, eight rows per warp of the team): the previous block J-1 as one
+          // more far unit.  Its values are the rows the chain warp produced in the step before plus the last row of the
+          // chunk above (row 0, fetched by the warp that uses it).
+          const int j = kB * J + lane;
+          float ecol[kB];
+          {
+            const int k0 = kB + lane - 1;              // transition index from the previous block's first vertex
+            const float *epn = E + (int64_t)(kB * (J - 1)) * Tl + k0;
+            const bool jok = j < O;
+#pragma unroll
+            for (int ii = 0; ii < kB; ii++) ecol[ii] = (jok && k0 - ii < Tl) ? __ldg(epn + (int64_t)ii * (Tl - 1)) : ninf;
+          }
+          if (sub == 0) {
+            pv[lane] = __ldcg(lat + (int64_t)(c * kB) * L + kB * (J - 1) + lane);
+            __syncwarp();
+          }
+          int *xkc = xk + (8 * sub) * kPitch + lane;
+          const float *pvr = pv + (8 * sub) * kEdPitch;
+#pragma unroll
+          for (int rr = 0; rr < 8; rr++) {
+            float b0 = key2f(xkc[rr * kPitch]), b1 = ninf;
+#pragma unroll
+            for (int c4 = 0; c4 < kB; c4 += 4) {
+              const float4 a4 = *reinterpret_cast<const float4 *>(pvr + rr * kEdPitch + c4);
+              b0 = max3(b0, a4.x + ecol[c4 + 0], a4.y + ecol[c4 + 1]);
+              b1 = max3(b1, a4.z + ecol[c4 + 2], a4.w + ecol[c4 + 3]);
+            }
+            xkc[rr * kPitch] = f2key(fmaxf(b0, b1));
+          }
+        }
+        if (sub == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");     // this tile's operands (staged one step ago)
+        team_sync(ts);
+#ifdef DAGB200_V3_TIMING
+        { long long tq = clock64(); if (tlog && warp == 0) g_v3t[sg][3] = tq - tstep0; }
+#endif
+        if (sub == 0) {
+          // ---- phase B (lanes = rows): column sweep over the diagonal block
           const int s = c * kB + lane;
-          const bool rowvalid = s < g.nsteps;
           const int t = 1 + s;
           const int jmax = g.full ? L : (O - 1 - (Tn - 1 - t));
-          const float *iow = io + lane * kPitch;
+          uint32_t vmask = 0;
+          {
+            const int lo = max(t, kB * J) - kB * J, hi = min(min(O - 1, jmax), kB * J + kB - 1) - kB * J;
+            if (s < g.nsteps && hi >= lo) vmask = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+          }
+          float *iow = io + lane * kIoPitch;
           const int *xkw = xk + lane * kPitch;
-          const bool prev_on = J > c;                // the previous block holds cells of this chunk
-          float vrow[kB];
-          chain_group<0>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, kB * J, t, O, jmax, prev_on);
-          chain_group<8>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, kB * J, t, O, jmax, prev_on);
-          chain_group<16>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, kB * J, t, O, jmax, prev_on);
-          chain_group<24>(vrow, vprev, ed, ep, iow, xkw, handin, handout, lane, rowvalid, kB * J, t, O, jmax, prev_on);
-          __syncwarp();
-          // reset the far maxima for the step after next; cell values -> staging tile -> lattice rows (coalesced)
+          {
+            float hd[kB];
 #pragma unroll
-          for (int k = 0; k < kB; k++) {
-            xk[lane * kPitch + k] = f2key(ninf);
-            io[lane * kPitch + k] = vrow[k];
-            vprev[k] = vrow[k];
+            for (int k = 0; k < kB; k++) hd[k] = ninf;
+            chain_group<0>(hd, ed, iow, xkw, handin, handout, lane, vmask);
+            chain_group<8>(hd, ed, iow, xkw, handin, handout, lane, vmask);
+            chain_group<16>(hd, ed, iow, xkw, handin, handout, lane, vmask);
+            chain_group<24>(hd, ed, iow, xkw, handin, handout, lane, vmask);
           }
           __syncwarp();
+#ifdef DAGB200_V3_TIMING
+          { long long tq = clock64(); if (tlog && warp == 0) g_v3t[sg][7] = tq - tstep0; }
+#endif
+          // ---- phase C: reset the far maxima for the step after next; my rows become source rows 1..31 of the next
+          // block's phase A; cell values -> lattice rows (coalesced)
+#pragma unroll
+          for (int k = 0; k < kB; k++) xk[lane * kPitch + k] = f2key(ninf);
+          if (lane < kB - 1) {
+#pragma unroll
+            for (int k = 0; k < kB; k += 4)
+              *reinterpret_cast<float4 *>(pv + (lane + 1) * kEdPitch + k) = *reinterpret_cast<const float4 *>(iow + k);
+          }
           {
             const int rl = min(kB, g.nsteps - c * kB);
             const int j = kB * J + lane;
-            if (j < L)
-              for (int rr = 0; rr < rl; rr++) __stcg(lat + (int64_t)(1 + c * kB + rr) * L + j, io[rr * kPitch + lane]);
-            // what my last row hands to the chunk below (next local chunk: the other CTA; last chunk: next pass)
+            if (j < L) {
+#pragma unroll 8
+              for (int rr = 0; rr < kB; rr++)
+                if (rr < rl) __stcg(lat + (int64_t)(1 + c * kB + rr) * L + j, io[rr * kIoPitch + lane]);
+            }
+            // what my last row hands to the chunk below (next local chunk: the other CTA or this one; last chunk: next pass)
             const int slot = (lc + 1) % kPassChunks;
             __stcg(HG + (size_t)slot * NB * kB + kB * J + lane, handout[lane]);
           }
           __syncwarp();
-          // operands of my next tile
-          staged = false;
-          if (g.tile_alive(c, J + 1)) { chain_stage(g, m, E, ed, ep, io, c, J + 1, lane); staged = true; }
+#ifdef DAGB200_V3_TIMING
+          { long long tq = clock64(); if (tlog && warp == 0) g_v3t[sg][1] = tq - tstep0; }
+#endif
+        } else if (sub == 1) {
+          // operands of the team's next tile into the other buffer, while the chain warp sweeps this one
+          if (g.tile_alive(c, J + 1))
+            chain_stage(g, m, E, s_ed + (((J + 1) & 1) * kChain + ts) * kB * kEdPitch,
+                        s_io + (((J + 1) & 1) * kChain + ts) * kB * kIoPitch, c, J + 1, lane, vec_m);
+        } else if (sub == 2) {
+          // the transition column of the next tile's phase A towards L2: row 32 J + lane of the links plane,
+          // transitions 31 - lane .. 62 - lane
+          if (g.tile_alive(c, J + 1) && kB * J + lane < O) {
+            const float *pf = E + (int64_t)(kB * J + lane) * Tl + (kB - 1 - lane);
+#pragma unroll
+            for (int x = 0; x < 40; x += 8)
+              if (kB - 1 - lane + min(x, 31) < Tl) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + min(x, 31)));
+          }
         }
-      } else {
-        // ======================= far warps: far maxima of the NEXT step's tiles ===================================
+      }
+      {
+        // ======================= every warp: far maxima of the NEXT step's tiles ===================================
+        // Units (tile, source block, half) are pulled from a per-step counter in shared memory.
         const int sn = sg + 1;
         if (sn < nst) {
           int nun[kChain], total = 0;
 #pragma unroll
-          for (int ts = 0; ts < kChain; ts++) {
-            const int lc = 2 * ts + rank, c = kPassChunks * p + lc, J = sn - lc;
-            nun[ts] = (lc < cpass && g.tile_alive(c, J)) ? max(0, J - 2 - g.ilo(c, J) + 1) : 0;
-            total += nun[ts];
+          for (int x = 0; x < kChain; x++) {
+            const int lcx = chunk_of(x, rank), cx = kPassChunks * p + lcx, Jx = sn - lcx;
+            nun[x] = (lcx < cpass && g.tile_alive(cx, Jx)) ? 2 * max(0, Jx - 2 - g.ilo(cx, Jx) + 1) : 0;
+            total += nun[x];
           }
-          const int u0 = (int)(((int64_t)total * fw) / kFar), u1 = (int)(((int64_t)total * (fw + 1)) / kFar);
-          if (u1 > u0) {
-            auto decode = [&](int u, int &ts, int &I) {
-              ts = 0;
-              int r = u;
+          int *qnext = s_queue + (sn & 1);
+          auto grab = [&]() {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(qnext, 1);
+            return __shfl_sync(0xffffffffu, u, 0);
+          };
+          // unit -> (tile slot, first source vertex of the half block)
+          auto decode = [&](int u, int &tx, int &i0) {
+            tx = 0;
+            int r = u;
 #pragma unroll
-              for (int x = 0; x < kChain - 1; x++)
-                if (ts == x && r >= nun[x]) { r -= nun[x]; ts = x + 1; }
-              const int lc = 2 * ts + rank, c = kPassChunks * p + lc, J = sn - lc;
-              I = g.ilo(c, J) + r;
-            };
-            auto stage = [&](int u, float *slab) {
-              int ts, I;
-              decode(u, ts, I);
-              const int c = kPassChunks * p + 2 * ts + rank;
-              const int tp0 = c * kB;                       // previous-row index of the tile's first row
-              if (vec_ok) {
-                const int q = lane & 7;
-                for (int rr = lane >> 3; rr < kB; rr += 4) {
-                  float *dst = slab + rr * kB + 4 * q;
-                  if (tp0 + rr < g.nsteps) cp_async16_cg(dst, lat + (int64_t)(tp0 + rr) * L + kB * I + 4 * q);
-                  else *reinterpret_cast<float4 *>(dst) = make_float4(ninf, ninf, ninf, ninf);
-                }
-              } else {
-                const float *lp = lat + (int64_t)tp0 * L + kB * I + lane;       // 32 I + lane < 32 J <= O - 1 < L
-                for (int rr = 0; rr < kB; rr++) slab[rr * kB + lane] = (tp0 + rr < g.nsteps) ? __ldcg(lp + (int64_t)rr * L) : ninf;
+            for (int x = 0; x < kChain - 1; x++)
+              if (tx == x && r >= nun[x]) { r -= nun[x]; tx = x + 1; }
+            const int lcx = chunk_of(tx, rank), cx = kPassChunks * p + lcx, Jx = sn - lcx;
+            i0 = kB * g.ilo(cx, Jx) + kHalf * r;
+          };
+          auto stage = [&](int u, float *slab) {
+            int tx, i0;
+            decode(u, tx, i0);
+            const int tp0 = (kPassChunks * p + chunk_of(tx, rank)) * kB;       // previous-row index of the tile's first row
+            if (vec_ok) {
+              const int q = lane & 3;
+#pragma unroll
+              for (int rr = lane >> 2; rr < kB; rr += 8) {
+                float *dst = slab + rr * kHalf + 4 * q;
+                if (tp0 + rr < g.nsteps) cp_async16_cg(dst, lat + (int64_t)(tp0 + rr) * L + i0 + 4 * q);
+                else *reinterpret_cast<float4 *>(dst) = make_float4(ninf, ninf, ninf, ninf);
               }
-              asm volatile("cp.async.commit_group;" ::: "memory");
-            };
+            } else {
+              const int q = lane & 15;
+              const float *lp = lat + (int64_t)tp0 * L + i0 + q;              // i0 + q < 32 J <= O - 1 < L
+              for (int rr = lane >> 4; rr < kB; rr += 2) slab[rr * kHalf + q] = (tp0 + rr < g.nsteps) ? __ldcg(lp + (int64_t)rr * L) : ninf;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          };
+          int cur = (total > 0) ? grab() : total;
+          if (cur < total) {
             float acc[kB];
 #pragma unroll
             for (int k = 0; k < kB; k++) acc[k] = ninf;
-            int cur_ts = -1;
-            auto flush = [&](int ts) {
-              int *xk = s_xk + ((sn & 1) * kChain + ts) * kB * kPitch + lane;
-#pragma unroll
-              for (int k = 0; k < kB; k++) {
-                if (acc[k] > ninf) atomicMax(xk + k * kPitch, f2key(acc[k]));
-                acc[k] = ninf;
-              }
-            };
             int buf = 0;
-            stage(u0, vs0);
-            for (int u = u0; u < u1; u++) {
-              const bool more = u + 1 < u1;
-              if (more) stage(u + 1, vs0 + (buf ^ 1) * kB * kB);
-              int ts, I;
-              decode(u, ts, I);
-              if (ts != cur_ts) { if (cur_ts >= 0) flush(cur_ts); cur_ts = ts; }
-              const int J = sn - (2 * ts + rank);
-              const int j = kB * J + lane;
-              float ecol[kB];
+            stage(cur, vs0);
+            while (cur < total) {
+              const int nxt = grab();
+              const bool more = nxt < total;
+              if (more) stage(nxt, vs0 + (buf ^ 1) * kB * kHalf);
+              int tx, i0;
+              decode(cur, tx, i0);
+              const int j = kB * (sn - chunk_of(tx, rank)) + lane;
+              float ecol[kHalf];
               {
-                const int k0 = j - kB * I - 1;                // transition index from the block's first source vertex; >= 32
-                const float *epn = E + (int64_t)(kB * I) * Tl + k0;
+                const int k0 = j - i0 - 1;                    // transition index from the half block's first source vertex; >= 32
+                const float *epn = E + (int64_t)i0 * Tl + k0;
                 const bool jok = j < O;
 #pragma unroll
-                for (int ii = 0; ii < kB; ii++) ecol[ii] = (jok && k0 - ii < Tl) ? __ldg(epn + (int64_t)ii * (Tl - 1)) : ninf;
+                for (int ii = 0; ii < kHalf; ii++) ecol[ii] = (jok && k0 - ii < Tl) ? __ldg(epn + (int64_t)ii * (Tl - 1)) : ninf;
               }
               if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
               else asm volatile("cp.async.wait_group 0;" ::: "memory");
               __syncwarp();
-              const float *vsw = vs0 + buf * kB * kB;
+              const float4 *vsw = reinterpret_cast<const float4 *>(vs0 + buf * kB * kHalf);
+              // the four broadcast loads of a row are issued one row ahead of the arithmetic that consumes them
+              float4 a0 = vsw[0], a1 = vsw[1], a2 = vsw[2], a3 = vsw[3];
 #pragma unroll
               for (int rr = 0; rr < kB; rr++) {
-                float b0 = acc[rr], b1 = ninf;
-#pragma unroll
-                for (int c4 = 0; c4 < kB; c4 += 4) {
-                  const float4 a4 = *reinterpret_cast<const float4 *>(vsw + rr * kB + c4);
-                  b0 = max3(b0, a4.x + ecol[c4 + 0], a4.y + ecol[c4 + 1]);
-                  b1 = max3(b1, a4.z + ecol[c4 + 2], a4.w + ecol[c4 + 3]);
-                }
+                float4 n0 = a0, n1 = a1, n2 = a2, n3 = a3;
+                if (rr + 1 < kB) { n0 = vsw[4 * (rr + 1)]; n1 = vsw[4 * (rr + 1) + 1]; n2 = vsw[4 * (rr + 1) + 2]; n3 = vsw[4 * (rr + 1) + 3]; }
+                float b0 = acc[rr], b1;
+                b0 = max3(b0, a0.x + ecol[0], a0.y + ecol[1]);
+                b1 = fmaxf(a0.z + ecol[2], a0.w + ecol[3]);
+                b0 = max3(b0, a1.x + ecol[4], a1.y + ecol[5]);
+                b1 = max3(b1, a1.z + ecol[6], a1.w + ecol[7]);
+                b0 = max3(b0, a2.x + ecol[8], a2.y + ecol[9]);
+                b1 = max3(b1, a2.z + ecol[10], a2.w + ecol[11]);
+                b0 = max3(b0, a3.x + ecol[12], a3.y + ecol[13]);
+                b1 = max3(b1, a3.z + ecol[14], a3.w + ecol[15]);
                 acc[rr] = fmaxf(b0, b1);
+                a0 = n0; a1 = n1; a2 = n2; a3 = n3;
               }
               __syncwarp();
               buf ^= 1;
+              // my next unit belongs to another tile (or there is none): the maxima of this tile meet the other warps'
+              int txn = -1, i0n = 0;
+              if (more) decode(nxt, txn, i0n);
+              if (txn != tx) {
+                int *xk = s_xk + ((sn & 1) * kChain + tx) * kB * kPitch + lane;
+#pragma unroll
+                for (int k = 0; k < kB; k++) {
+                  if (acc[k] > ninf) atomicMax(xk + k * kPitch, f2key(acc[k]));
+                  acc[k] = ninf;
+                }
+              }
+              cur = nxt;
             }
-            flush(cur_ts);
           }
         }
+        if (threadIdx.x == 0) s_queue[sg & 1] = 0;     // the counter of the step after next (nobody touches it in this step)
       }
+#ifdef DAGB200_V3_TIMING
+      const long long tbusy = clock64() - tstep0;
+#endif
       cluster_sync_all();      // the step is complete in both CTAs and visible to both
+#ifdef DAGB200_V3_TIMING
+      if (tlog) {
+        if (warp == 0) g_v3t[sg][0] = tbusy;
+        if (warp == 4) { g_v3t[sg][2] = clock64() - tstep0; }
+        if (warp == 15) g_v3t[sg][4] = tbusy;
+        if (warp == 2) g_v3t[sg][5] = tbusy;
+      }
+#endif
     }
   }
 
@@ -389,6 +522,10 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
   // the path all threads of CTA 0 score its candidates delta = 1 .. min(pos, Tl) that hold a lattice cell (source
   // vertex >= i-1; the others are -inf) -- ONE fp32 add each, as in the forward sweep -- and reduce them with the
   // reference's order (value, then class priority, then smaller delta).
+#ifdef DAGB200_V3_TIMING
+  const long long tbt0 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_v3t[62][0] = tbt0 - tkernel0;
+#endif
   if (rank == 0) {
     float *s_bv = reinterpret_cast<float *>(v3_smem);
     int *s_bd = reinterpret_cast<int *>(v3_smem) + kWarps;
@@ -400,15 +537,31 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
       code = DAGB200_ST_NO_PATH;
     } else {
       for (int i = Tn - 1; i >= 1; i--) {
+#ifdef DAGB200_V3_TIMING
+        const long long tbl0 = clock64();
+#endif
         if (threadIdx.x == 0) prow[pos] = i;
         const float *prev = lat + (int64_t)(i - 1) * L;
         const int dmax = min(min(pos, Tl), pos - (i - 1));
         float bv = ninf; int bd = 0;
         for (int d = dmax - (int)threadIdx.x; d >= 1; d -= kThreads) {    // descending delta inside a thread
           const int src = pos - d;
-          const float x = __ldcg(prev + src) + __ldg(E + (int64_t)src * Tl + d - 1);
+          const float *ep = E + (int64_t)src * Tl + d - 1;
+          const float x = __ldcg(prev + src) + __ldg(ep);
+          // the next row asks the same source vertices for a transition a few columns to the left (the path moves left by
+          // the delta chosen here) and for their values one row up: pull both towards L2 now, off the dependency chain
+          if (i >= 2) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep - min(d - 1, 8)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep - min(d - 1, 16)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(prev - L + src));
+          }
           if (better(x, d, bv, bd)) { bv = x; bd = d; }
         }
+#ifdef DAGB200_V3_TIMING
+        long long tb1;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(tb1) : "f"(bv) : "memory");
+        if (blockIdx.x == 0 && threadIdx.x == 0) { g_v3t[62][2] += tb1 - tbl0; }
+#endif
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -436,6 +589,9 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
       if (code == DAGB200_ST_OK && threadIdx.x == 0) prow[pos] = 0;
     }
     if (status && threadIdx.x == 0) status[b] = code;
+#ifdef DAGB200_V3_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_v3t[62][1] = clock64() - tbt0;
+#endif
   }
 }
 
@@ -443,8 +599,8 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
 
 size_t vit3_smem_bytes() {
   using namespace v3;
-  return sizeof(float) * ((size_t)2 * kChain * kB * kB + (size_t)3 * kChain * kB * kPitch + kChain * 2 * kB +
-                          (size_t)kFar * 2 * kB * kB) + 16;
+  return sizeof(float) * ((size_t)5 * kChain * kB * kEdPitch + (size_t)2 * kChain * kB * kPitch + kChain * 2 * kB + 4 +
+                          (size_t)kWarps * 2 * kB * kHalf) + 16;
 }
 size_t vit3_hand_bytes(int B, int L) {
   const int NB = (L + 31) / 32;
@@ -462,6 +618,19 @@ int launch_viterbi_wave(const float *match, const float *links, const int64_t *o
   dag_viterbi_wave_kernel<<<2 * B, kThreads, smem, st>>>(match, links, olen, tlen, lattice, path, hand_g, M, L, Tl, NB,
                                                         full_lattice, status);
   DAGB200_CHECK_LAUNCH("dag_viterbi_wave_kernel");
+#ifdef DAGB200_V3_TIMING
+  {
+    static int calls = 0;
+    if (++calls == 3) {
+      cudaStreamSynchronize(st);
+      long long h[64][8];
+      cudaMemcpyFromSymbol(h, g_v3t, sizeof(h));
+      printf("[v3 timing, CTA 0] step: warp0 busy, warp2 busy, warp15 busy, step length | chain warp 0, since step start: team barrier passed, -, sweep done, stored\n");
+      printf("  forward (prologue + steps) %lld cycles, backtrace %lld cycles (candidate loads of thread 0: %lld over 3 launches)\n", h[62][0], h[62][1], h[62][2]);
+      for (int i = 0; i < 40; i++) printf("  %2d  %7lld %7lld %7lld %7lld | %7lld %7lld %7lld %7lld\n", i, h[i][0], h[i][5], h[i][4], h[i][2], h[i][3], h[i][6], h[i][7], h[i][1]);
+    }
+  }
+#endif
   prof_mark(7, st);
   return 0;
 }

@@ -8,6 +8,12 @@ The criterion (DASpeech/criterions/nat_dag_loss.py:130-132) pins every glanced v
 
 `glat_force_emit(match_all, matchmask, keep_word_mask)` is the same function (values and gradient) as one streaming
 kernel each way (`dagb200_glat_force_emit`, dag_glat.cu).  No CPU path.
+
+`glat_alignment(match, links, output_length, target_length, tgt_tokens, pred_tokens)` is the Viterbi alignment of the
+glancing pass together with everything the criterion derives from the path (nat_dag_loss.py:221-227: `path`,
+`predict_align_mask`, `matchmask`, `oracle`, `same_num`): the Viterbi kernel followed by ONE kernel that writes the
+[B, M, L] mask plane exactly once (`dagb200_glat_alignment`) instead of a [B, M+1, L] zero fill, a scatter, a slice, a
+gather and a masked reduction.
 """
 import torch
 
@@ -46,3 +52,32 @@ class GlatForceEmitFunc(torch.autograd.Function):
 
 
 glat_force_emit = GlatForceEmitFunc.apply
+
+
+def glat_alignment(match, links, output_length, target_length, tgt_tokens, pred_tokens=None):
+    """Returns dict(path [B,L] long, predict_align_mask [B,L] bool, matchmask [B,M,L] bool, oracle [B,L] long,
+    same_num [B] long or None).  Non-differentiable, like `dag_best_alignment` (custom_ops/dag_loss.py:190-236)."""
+    from .custom_ops.dag_loss import get_dag_kernel, DagBestAlignmentFunc
+    with torch.no_grad():
+        k = get_dag_kernel()
+        match = match.detach().contiguous()
+        links = links.detach().contiguous()
+        _, path32 = k.dag_best_alignment(match, links, output_length, target_length, DagBestAlignmentFunc.config,
+                                         want_alpha=False)
+        B, M, L = match.shape
+        _check(tgt_tokens.shape == (B, M) and tgt_tokens.dtype == torch.long, "tgt_tokens should be long [bsz, tarlen]")
+        if pred_tokens is not None:
+            _check(pred_tokens.shape == (B, L) and pred_tokens.dtype == torch.long, "pred_tokens should be long [bsz, prelen]")
+            pred_tokens = pred_tokens.contiguous()
+        dev = match.device
+        matchmask = torch.empty((B, M, L), dtype=torch.bool, device=dev)
+        oracle = torch.empty((B, L), dtype=torch.long, device=dev)
+        path = torch.empty((B, L), dtype=torch.long, device=dev)
+        align = torch.empty((B, L), dtype=torch.bool, device=dev)
+        same = torch.empty((B,), dtype=torch.long, device=dev) if pred_tokens is not None else None
+        with torch.cuda.device(dev):
+            rc = _lib.load().dagb200_glat_alignment(_ptr(path32), _ptr(tgt_tokens), tgt_tokens.stride(0), tgt_tokens.stride(1),
+                                                    _ptr(pred_tokens), _ptr(matchmask), _ptr(oracle), _ptr(path), _ptr(align),
+                                                    _ptr(same), B, M, L, _stream())
+        _lib.check(rc, "glat_alignment")
+    return {"path": path, "predict_align_mask": align, "matchmask": matchmask, "oracle": oracle, "same_num": same}

@@ -163,6 +163,19 @@ int dagb200_dag_posterior(const float *alpha, const float *beta, void *score, in
 int dagb200_glat_force_emit(const float *match, const unsigned char *matchmask, const unsigned char *keep_word_mask,
                             float *out, int B, int M, int L, int backward, void *stream);
 
+/* Next row (remainder): what the glancing pass derives from the Viterbi path, replacing a
+ * [B][M+1][L] zero fill + scatter + slice, a gather and a masked reduction (criterions/nat_dag_loss.py:223-227):
+ *   matchmask[b][t][j] = (path[b][j] == t)                      bool [B][M][L], written exactly once
+ *   oracle[b][j]       = tgt_tokens[b][max(path[b][j], 0)]      int64 [B][L]        (nullable)
+ *   path64[b][j]       = path[b][j]                             int64 [B][L]        (nullable; the wrapper's .to(long))
+ *   align_mask[b][j]   = path[b][j] >= 0                        bool [B][L]         (nullable)
+ *   same_num[b]        = #{j : path >= 0 and pred_tokens[b][j] == oracle[b][j]}   int64 [B]   (nullable, needs pred_tokens)
+ * path is the int32 [B][L] output of dagb200_dag_best_alignment; tgt_tokens int64 addressed tgt[b*tsb + t*tss];
+ * pred_tokens int64 [B][L] contiguous (the arg-max of the vocabulary logits, nat_dag_loss.py:209).                     */
+int dagb200_glat_alignment(const int32_t *path, const int64_t *tgt_tokens, int64_t tsb, int64_t tss,
+                           const int64_t *pred_tokens, unsigned char *matchmask, int64_t *oracle, int64_t *path64,
+                           unsigned char *align_mask, int64_t *same_num, int B, int M, int L, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ from oracle import oracle
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DP_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith("gather"))
+                  if not os.path.basename(p).startswith(("gather", "criterion")))
 
 
 def test_exported_names_match_reference_surface():

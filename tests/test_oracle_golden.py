@@ -10,7 +10,7 @@ from oracle import oracle
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DP_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith("gather"))
+                  if not os.path.basename(p).startswith(("gather", "criterion")))
 GATHER_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "gather*.npz")))
 
 
