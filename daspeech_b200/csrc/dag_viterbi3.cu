@@ -521,15 +521,12 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
   // ---- backtrace (dag_best_alignment.cu:178-184) with the back-pointers recomputed on the way: for the cell (i, pos) of
   // the path all threads of CTA 0 score its candidates delta = 1 .. min(pos, Tl) that hold a lattice cell (source
   // vertex >= i-1; the others are -inf) -- ONE fp32 add each, as in the forward sweep -- and reduce them with the
-  // reference's order (value, then class priority, then smaller delta).
-#ifdef DAGB200_V3_TIMING
-  const long long tbt0 = clock64();
-  if (blockIdx.x == 0 && threadIdx.x == 0) g_v3t[62][0] = tbt0 - tkernel0;
-#endif
+  // reference's order: value, then class priority 0,2,1,3 of (delta-1) mod 4, then smaller delta.  The reduction is two
+  // warp-wide integer reductions (REDUX) on (value key) and (priority << 16 | delta) per level and ONE block barrier per
+  // step: every warp repeats the second level, so no result has to be broadcast.
   if (rank == 0) {
-    float *s_bv = reinterpret_cast<float *>(v3_smem);
-    int *s_bd = reinterpret_cast<int *>(v3_smem) + kWarps;
-    int *s_pos = s_bd + kWarps;
+    int *s_k1 = reinterpret_cast<int *>(v3_smem);            // [2 (step parity)][warps] best value key of a warp
+    int *s_k2 = s_k1 + 2 * kWarps;                           // [2][warps] its (priority << 16 | delta)
     __syncthreads();
     int code = DAGB200_ST_OK;
     int pos = O - 1;
@@ -537,61 +534,54 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
       code = DAGB200_ST_NO_PATH;
     } else {
       for (int i = Tn - 1; i >= 1; i--) {
-#ifdef DAGB200_V3_TIMING
-        const long long tbl0 = clock64();
-#endif
         if (threadIdx.x == 0) prow[pos] = i;
         const float *prev = lat + (int64_t)(i - 1) * L;
         const int dmax = min(min(pos, Tl), pos - (i - 1));
+        // my candidates: delta = dmax - tid, dmax - tid - 512, ... (descending); all loads first
         float bv = ninf; int bd = 0;
-        for (int d = dmax - (int)threadIdx.x; d >= 1; d -= kThreads) {    // descending delta inside a thread
-          const int src = pos - d;
-          const float *ep = E + (int64_t)src * Tl + d - 1;
-          const float x = __ldcg(prev + src) + __ldg(ep);
-          // the next row asks the same source vertices for a transition a few columns to the left (the path moves left by
-          // the delta chosen here) and for their values one row up: pull both towards L2 now, off the dependency chain
+        for (int d0 = dmax - (int)threadIdx.x; d0 >= 1; d0 -= 2 * kThreads) {
+          const int d1 = d0 - kThreads;
+          const float *e0 = E + (int64_t)(pos - d0) * Tl + d0 - 1;
+          const float *e1 = E + (int64_t)(pos - max(d1, 1)) * Tl + max(d1, 1) - 1;
+          const float v0 = __ldcg(prev + pos - d0), t0 = __ldg(e0);
+          const float v1 = d1 >= 1 ? __ldcg(prev + pos - d1) : ninf, t1 = d1 >= 1 ? __ldg(e1) : 0.f;
+          // the next row asks the same source vertices for a transition a few columns to the left (the path moves left
+          // by the delta chosen here) and for their values one row up: pull both towards L2 now
           if (i >= 2) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep - min(d - 1, 8)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(ep - min(d - 1, 16)));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(prev - L + src));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e0 - min(d0 - 1, 8)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(prev - L + pos - d0));
+            if (d1 >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(e1 - min(d1 - 1, 8)));
           }
-          if (better(x, d, bv, bd)) { bv = x; bd = d; }
+          const float x0 = v0 + t0, x1 = v1 + t1;
+          if (better(x0, d0, bv, bd)) { bv = x0; bd = d0; }
+          if (d1 >= 1 && better(x1, d1, bv, bd)) { bv = x1; bd = d1; }
         }
-#ifdef DAGB200_V3_TIMING
-        long long tb1;
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(tb1) : "f"(bv) : "memory");
-        if (blockIdx.x == 0 && threadIdx.x == 0) { g_v3t[62][2] += tb1 - tbl0; }
-#endif
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int od = __shfl_xor_sync(0xffffffffu, bd, o);
-          if (better(ov, od, bv, bd)) { bv = ov; bd = od; }
-        }
-        if (lane == 0) { s_bv[warp] = bv; s_bd[warp] = bd; }
-        __syncthreads();
-        if (warp == 0) {
-          bv = (lane < kWarps) ? s_bv[lane] : ninf;
-          bd = (lane < kWarps) ? s_bd[lane] : 0;
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int od = __shfl_xor_sync(0xffffffffu, bd, o);
-            if (better(ov, od, bv, bd)) { bv = ov; bd = od; }
-          }
-          if (lane == 0) s_pos[0] = (bv > ninf) ? bd : 0;
+        // level 1: the warp's best value, then the preferred delta among the lanes that hold it
+        const int par = (i & 1) * kWarps;
+        {
+          const int k1 = f2key(bv + 0.0f);                 // (-0 and +0 are one value)
+          const int w1 = __reduce_max_sync(0xffffffffu, k1);
+          const int k2 = (k1 == w1 && bv > ninf) ? ((rank4(bd) << 16) | bd) : 0x7fffffff;
+          const int w2 = __reduce_min_sync(0xffffffffu, k2);
+          if (lane == 0) { s_k1[par + warp] = w1; s_k2[par + warp] = w2; }
         }
         __syncthreads();
-        const int d = s_pos[0];
-        if (d == 0) { code = DAGB200_ST_NO_PATH; break; }
-        pos -= d;
+        // level 2, in every warp
+        int dsel;
+        {
+          const int k1 = lane < kWarps ? s_k1[par + lane] : f2key(ninf);
+          const int k2r = lane < kWarps ? s_k2[par + lane] : 0x7fffffff;
+          const int w1 = __reduce_max_sync(0xffffffffu, k1);
+          const int k2 = (k1 == w1) ? k2r : 0x7fffffff;
+          const int w2 = __reduce_min_sync(0xffffffffu, k2);
+          dsel = (w2 == 0x7fffffff) ? 0 : (w2 & 0xffff);
+        }
+        if (dsel == 0) { code = DAGB200_ST_NO_PATH; break; }
+        pos -= dsel;
       }
       if (code == DAGB200_ST_OK && threadIdx.x == 0) prow[pos] = 0;
     }
     if (status && threadIdx.x == 0) status[b] = code;
-#ifdef DAGB200_V3_TIMING
-    if (blockIdx.x == 0 && threadIdx.x == 0) g_v3t[62][1] = clock64() - tbt0;
-#endif
   }
 }
 
