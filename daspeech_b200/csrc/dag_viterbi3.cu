@@ -547,10 +547,18 @@ dag_viterbi_wave_kernel(const float *__restrict__ match, const float *__restrict
           const float v1 = d1 >= 1 ? __ldcg(prev + pos - d1) : ninf, t1 = d1 >= 1 ? __ldg(e1) : 0.f;
           // the next row asks the same source vertices for a transition a few columns to the left (the path moves left
           // by the delta chosen here) and for their values one row up: pull both towards L2 now
-          if (i >= 2) {
+#ifndef DAGB200_BT_PREFETCH
+#define DAGB200_BT_PREFETCH 0
+#endif
+          if (DAGB200_BT_PREFETCH >= 1 && i >= 2) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(e0 - min(d0 - 1, 8)));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(prev - L + pos - d0));
             if (d1 >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(e1 - min(d1 - 1, 8)));
+            if (DAGB200_BT_PREFETCH >= 2) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(e0 - min(d0 - 1, 16)));
+              if (d1 >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(e1 - min(d1 - 1, 16)));
+              if (i >= 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(prev - 2 * L + pos - d0));
+            }
           }
           const float x0 = v0 + t0, x1 = v1 + t1;
           if (better(x0, d0, bv, bd)) { bv = x0; bd = d0; }

@@ -80,7 +80,7 @@ class _DagKernel:
         self._scratch = {}
         self._pending = []      # (what, pinned host copy of the per-sample status, event) of earlier calls
         self._pinned = None
-        self._pin_next = 0
+        self._free = []
 
     # ---- per-sample device status (the reference's CUDA_KERNEL_ASSERTs, dag_loss.cu:68-69, dag_best_alignment.cu:67-70,118)
     # The status words are always produced (B int32).  DAGB200_DEBUG=1 checks them synchronously and raises; otherwise
@@ -90,29 +90,34 @@ class _DagKernel:
         if _DEBUG:
             _check_status(status)
             return
-        # a small ring of persistent pinned buffers: no host allocation on the launch path
+        # a small ring of persistent pinned buffers: no host allocation and NO host synchronisation on the launch path.
+        # When the host runs many calls ahead of the device the ring fills up; the status of those calls is then simply
+        # not tracked (the outputs still carry -inf / -1 for offending samples).
         n = status.numel()
-        if len(self._pending) >= 16:
-            self.check_pending_status(wait=True)
         if self._pinned is None or self._pinned.shape[1] < n:
             self.check_pending_status(wait=True)
-            self._pinned = torch.empty((17, max(n, 256)), dtype=torch.int32, pin_memory=True)
-            self._pin_next = 0
-        host = self._pinned[self._pin_next, :n]
-        self._pin_next = (self._pin_next + 1) % self._pinned.shape[0]
+            self._pinned = torch.empty((16, max(n, 256)), dtype=torch.int32, pin_memory=True)
+            self._free = list(range(16))
+        if not self._free:
+            return
+        slot = self._free.pop()
+        host = self._pinned[slot, :n]
         host.copy_(status, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self._pending.append((what, host, ev))
+        self._pending.append((what, host, ev, slot))
 
     def check_pending_status(self, wait=False):
         keep = []
-        for what, host, ev in self._pending:
+        blocked = False
+        for what, host, ev, slot in self._pending:
             if wait:
                 ev.synchronize()
-            if not ev.query():
-                keep.append((what, host, ev))
+            if blocked or not ev.query():      # oldest first: once one is still in flight the younger ones are not asked
+                blocked = True
+                keep.append((what, host, ev, slot))
                 continue
+            self._free.append(slot)
             bad = host.nonzero()
             if bad.numel():
                 b = int(bad[0])
