@@ -122,17 +122,17 @@ extern "C" void dagb200_set_exact(int on) { g_exact_mode = on ? 1 : 0; }
 extern "C" int dagb200_get_exact(void) { return g_exact_mode; }
 
 namespace dagb200 {
-size_t grad3_workspace_bytes(int B, int M, int L);
-bool grad3_supported(int M, int L);
-int launch_grad3(const float *go, const float *alpha, const float *beta, const float *match, const float *links,
+size_t grad4_workspace_bytes(int B, int M, int L);
+bool grad4_supported(int M, int L);
+int launch_grad4(const float *go, const float *alpha, const float *beta, const float *match, const float *links,
                  const int64_t *olen, const int64_t *tlen, float *gm, float *gl, int B, int M, int L, int Tl,
                  void *workspace, cudaStream_t st);
 }  // namespace dagb200
 
 extern "C" size_t dagb200_dag_loss_backward_workspace_bytes(int B, int M, int L, int T) {
   (void)T;
-  if (B <= 0 || M < 2 || L < 1 || !dagb200::grad3_supported(M, L)) return 0;
-  return dagb200::grad3_workspace_bytes(B, M, L);
+  if (B <= 0 || M < 2 || L < 1 || !dagb200::grad4_supported(M, L)) return 0;
+  return dagb200::grad4_workspace_bytes(B, M, L);
 }
 
 extern "C" int dagb200_dag_loss_backward(const void *grad_output, const void *alpha, const void *beta,
@@ -141,7 +141,7 @@ extern "C" int dagb200_dag_loss_backward(const void *grad_output, const void *al
                                          int B, int M, int L, int T, int config1, int config2, void *stream);
 
 // Same contract as dagb200_dag_loss_backward plus a device scratch of dagb200_dag_loss_backward_workspace_bytes()
-// bytes: with it (fp32, not in exact mode) the two-pass plane kernels of dag_grad3.cu run.
+// bytes: with it (fp32, not in exact mode) the two-pass plane kernels of dag_grad4.cu run.
 extern "C" int dagb200_dag_loss_backward_ws(const void *grad_output, const void *alpha, const void *beta,
                                             const void *match, const void *links, const int64_t *output_length,
                                             const int64_t *target_length, void *grad_match, void *grad_links, int dtype,
@@ -149,14 +149,14 @@ extern "C" int dagb200_dag_loss_backward_ws(const void *grad_output, const void 
                                             size_t workspace_bytes, void *stream) {
   using namespace dagb200;
   const bool fast = dtype == DAGB200_F32 && !g_exact_mode && workspace && B > 0 && M >= 2 && L >= 1 && T >= 1 &&
-                    grad3_supported(M, L) && workspace_bytes >= grad3_workspace_bytes(B, M, L) &&
+                    grad4_supported(M, L) && workspace_bytes >= grad4_workspace_bytes(B, M, L) &&
                     config1 >= 1 && config1 <= 2 && config2 >= 1 && config2 <= 3 && grad_output && alpha && beta && match &&
                     links && output_length && target_length && grad_match && grad_links &&
                     (int64_t)L * T < (1ll << 31) && (int64_t)M * L < (1ll << 31) && B < 65536 && M < 65536;
   if (!fast)
     return dagb200_dag_loss_backward(grad_output, alpha, beta, match, links, output_length, target_length, grad_match,
                                      grad_links, dtype, B, M, L, T, config1, config2, stream);
-  return launch_grad3((const float *)grad_output, (const float *)alpha, (const float *)beta, (const float *)match,
+  return launch_grad4((const float *)grad_output, (const float *)alpha, (const float *)beta, (const float *)match,
                       (const float *)links, output_length, target_length, (float *)grad_match, (float *)grad_links, B, M,
                       L, T, workspace, (cudaStream_t)stream);
 }
