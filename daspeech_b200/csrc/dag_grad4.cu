@@ -24,9 +24,9 @@
 //             copies into TENSOR MEMORY (tcgen05.st, double-buffered); the MMAs take A from there
 //             (tcgen05.mma ... [d], [a], b-desc) and B from shared memory, where it arrives by one bulk copy per step
 //             (3-stage mbarrier ring).  bf16 hi/lo split on both operands: 3 MMAs per product (M128 N32 K16), 12 per
-//             step, one issuing thread.  Epilogue: accumulators -> registers -> shared memory (thread = row) -> one
-//             coalesced pass per row that multiplies by exp2(links log2e + Fmax - Z log2e) and writes grad_links once,
-//             including the zero padding.
+//             step, one issuing thread.  The links tile of the epilogue is staged in shared memory by cp.async while
+//             the contraction runs; the row owners multiply their accumulators by exp2(links log2e + Fmax - Z log2e) in
+//             place, and one coalesced pass per row writes grad_links once, including the zero padding.
 #include <cstdio>
 #include <cstdlib>
 
@@ -362,7 +362,7 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
   if (n0 - (i0 + kBI - 1) - 1 >= Tl) return;              // entirely beyond the transition band: no storage
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef DAGB200_G4_TIMING
-  const bool tlog = b == 0 && blockIdx.x == 1 && lane == 0;
+  const bool tlog = b == 0 && blockIdx.x == gridDim.x - NNt + 1 && lane == 0;
   const long long tk0 = clock64();
 #endif
   const int O = (int)olen[b], Tn = (int)tlen[b];
@@ -399,6 +399,9 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+#ifdef DAGB200_G4_TIMING
+  if (warp == 0) G4T(11, clock64() - tk0);
+#endif
   const uint32_t tmem = *tmem_s;
   const int *FA = reinterpret_cast<const int *>(ws + pl.off_fa) + (size_t)b * (M + 1) * pl.NBp;
   const int *FB = reinterpret_cast<const int *>(ws + pl.off_fb) + (size_t)b * (M + 1) * pl.NBp;
@@ -407,11 +410,6 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
   if (compute) {
     if (warp == 5) {
       // ================================ bulk-copy producer (one thread): the eight B tiles of a step ==============
-      // the links tile the epilogue reads: 128 rows x 1 KB, towards L2 now
-      for (int x = lane; x < kBI * kNBt; x += 32) {
-        const int ii = x / kNBt, i = i0 + ii, k = n0 + (x % kNBt) * 32 - i - 1;
-        if (i < O && k + 31 >= 0 && k < Tl) asm volatile("prefetch.global.L2 [%0];" ::"l"(E + (int64_t)i * Tl + max(k, 0)));
-      }
       if (lane == 0) {
         const unsigned char *Bb = ws + pl.off_b + (size_t)b * pl.sample_b + (size_t)(n0 / 32) * 2048;
         for (int c = 0; c < nchunks; c++) {
@@ -476,6 +474,19 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
       const int nbl = lane >> 3, rp = lane & 7;
       const int fmx_l = __shfl_sync(0xffffffffu, fmx, nbl);
       const int Nl = n0 / 32 + nbl;
+      // the links tile of the epilogue travels to shared memory (the staging tile of the output) while the contraction
+      // runs: 4-byte asynchronous copies (the rows are not 16-byte aligned), lanes = consecutive transitions
+      for (int x = tid; x < kBI * kBN; x += 128) {
+        const int ii = x / kBN, nn = x % kBN;
+        const int ir = i0 + ii, n = n0 + nn, k = n - ir - 1;
+        float *dst = cs + ii * kCsPitch + nn;
+        if (ir < O && n < O && k >= 0 && k < Tl) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(E + (int64_t)ir * Tl + k) : "memory");
+        } else {
+          *dst = neg_inf_f();
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
       uint4 raw[4];
       {
         const uint4 *src = reinterpret_cast<const uint4 *>(Ab);
@@ -495,6 +506,9 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
         }
       };
       load_frames(0);
+#ifdef DAGB200_G4_TIMING
+      if (warp == 0) G4T(10, clock64() - tk0);
+#endif
       for (int c = 0; c < nchunks; c++) {
         const int ab = c & 1;
 #ifdef DAGB200_G4_TIMING
@@ -555,15 +569,19 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
       const long long tm0 = clock64();
       if (warp == 0) G4T(6, tm0 - tk0);
 #endif
-      // ---- accumulators -> shared memory, scaled by nothing yet (thread = row)
+      // ---- accumulators (thread = row) x exp2(links log2e + Fmax - Z log2e) x go, in place over the staged links tile
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // every scale thread's share of the links tile has landed
       mbar_wait(dfull, 0);
       tc_fence_after();
 #pragma unroll 1
       for (int nb = 0; nb < kNBt; nb++) {
         float v[32];
         tmem_ld32(tmem + nb * 32 + ((uint32_t)(warp * 32) << 16), v);
+        const float dp = dpair[warp * kNBt + nb];
+        float *row = cs + tid * kCsPitch + nb * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j++) cs[tid * kCsPitch + nb * 32 + j] = v[j];
+        for (int j = 0; j < 32; j++) row[j] = gout * exp2f(fmaf(row[j], kL2E, dp)) * v[j];
       }
       tc_fence_before();
 #ifdef DAGB200_G4_TIMING
@@ -578,40 +596,19 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
 
   // ---- epilogue: gl = go * exp2(links * log2e + Fmax - Z log2e) * G, one coalesced write per row, zeros elsewhere.
   const bool last_col = (n0 + kBN >= L);
-  // Four rows per warp at a time: their 32 transition values are all in flight before the first is used.
-  constexpr int kRows = 4, kWarpsAll = kThreads / 32;
-  for (int base = warp * kRows; base < kBI; base += kWarpsAll * kRows) {
-    float ev[kRows][kNBt];
+  for (int ii = warp; ii < kBI; ii += kThreads / 32) {
+    const int i = i0 + ii;
+    if (i >= L) break;
+    float *grow = g + (int64_t)i * Tl;
+    const bool rowon = compute && i < O;
 #pragma unroll
-    for (int r = 0; r < kRows; r++) {
-      const int ii = base + r, i = i0 + ii;
-      const float *erow = E + (int64_t)i * Tl;
-      const bool rowon = compute && i < O && ii < kBI;
-#pragma unroll
-      for (int h = 0; h < kNBt; h++) {
-        const int n = n0 + lane + 32 * h, k = n - i - 1;
-        ev[r][h] = (rowon && n < O && k >= 0 && k < Tl) ? __ldg(erow + k) : neg_inf_f();
-      }
+    for (int h = 0; h < kNBt; h++) {
+      const int nn = lane + 32 * h;
+      const int n = n0 + nn, k = n - i - 1;
+      if (k >= 0 && k < Tl) grow[k] = (rowon && n < O) ? cs[ii * kCsPitch + nn] : 0.f;
     }
-#pragma unroll
-    for (int r = 0; r < kRows; r++) {
-      const int ii = base + r, i = i0 + ii;
-      if (ii >= kBI || i >= L) break;
-      float *grow = g + (int64_t)i * Tl;
-      const bool rowon = compute && i < O;
-#pragma unroll
-      for (int h = 0; h < kNBt; h++) {
-        const int nn = lane + 32 * h;
-        const int n = n0 + nn, k = n - i - 1;
-        if (k >= 0 && k < Tl) {
-          float v = 0.f;
-          if (rowon && n < O) v = gout * exp2f(fmaf(ev[r][h], kL2E, dpair[(ii >> 5) * kNBt + h])) * cs[ii * kCsPitch + nn];
-          grow[k] = v;
-        }
-      }
-      if (last_col) {  // transitions that point beyond the padded graph: k >= L-1-i
-        for (int k = max(0, n0 + kBN - i - 1) + lane; k < Tl; k += 32) grow[k] = 0.f;
-      }
+    if (last_col) {  // transitions that point beyond the padded graph: k >= L-1-i
+      for (int k = max(0, n0 + kBN - i - 1) + lane; k < Tl; k += 32) grow[k] = 0.f;
     }
   }
   tc_fence_before();
@@ -665,8 +662,8 @@ int launch_grad4(const float *go, const float *alpha, const float *beta, const f
         cudaStreamSynchronize(st);
         long long h[16];
         cudaMemcpyFromSymbol(h, g_g4t, sizeof(h));
-        printf("[g4 timing, tile 1 of utterance 0, sums over 3 launches] issuer: wait B %lld, wait A %lld, issue %lld | scale warp 0: table+loads %lld, wait buffer %lld, scale+st %lld | main loop %lld, acc->smem %lld, epilogue %lld, total %lld\n",
-               h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+        printf("[g4 timing, tile 1 of utterance 0, sums over 3 launches] issuer: wait B %lld, wait A %lld, issue %lld | scale warp 0: table+loads %lld, wait buffer %lld, scale+st %lld | main loop %lld, acc->smem %lld, epilogue %lld, total %lld | after alloc+sync %lld, at loop start %lld\n",
+               h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[11], h[10]);
       }
     }
 #endif
