@@ -599,15 +599,17 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
   for (int ii = warp; ii < kBI; ii += kThreads / 32) {
     const int i = i0 + ii;
     if (i >= L) break;
-    float *grow = g + (int64_t)i * Tl;
     const bool rowon = compute && i < O;
+    const int kb = n0 + lane - i - 1;                        // transition index of my first column
+    float *gp = g + (int64_t)i * Tl + kb;
+    const float *cp = cs + ii * kCsPitch + lane;
 #pragma unroll
     for (int h = 0; h < kNBt; h++) {
-      const int nn = lane + 32 * h;
-      const int n = n0 + nn, k = n - i - 1;
-      if (k >= 0 && k < Tl) grow[k] = (rowon && n < O) ? cs[ii * kCsPitch + nn] : 0.f;
+      const int k = kb + 32 * h;
+      if (k >= 0 && k < Tl) gp[32 * h] = (rowon && n0 + lane + 32 * h < O) ? cp[32 * h] : 0.f;
     }
     if (last_col) {  // transitions that point beyond the padded graph: k >= L-1-i
+      float *grow = g + (int64_t)i * Tl;
       for (int k = max(0, n0 + kBN - i - 1) + lane; k < Tl; k += 32) grow[k] = 0.f;
     }
   }
