@@ -476,14 +476,21 @@ grad_links_tcgen05_kernel(const float *__restrict__ go, const float *__restrict_
       const int Nl = n0 / 32 + nbl;
       // the links tile of the epilogue travels to shared memory (the staging tile of the output) while the contraction
       // runs: 4-byte asynchronous copies (the rows are not 16-byte aligned), lanes = consecutive transitions
-      for (int x = tid; x < kBI * kBN; x += 128) {
-        const int ii = x / kBN, nn = x % kBN;
-        const int ir = i0 + ii, n = n0 + nn, k = n - ir - 1;
-        float *dst = cs + ii * kCsPitch + nn;
-        if (ir < O && n < O && k >= 0 && k < Tl) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(E + (int64_t)ir * Tl + k) : "memory");
-        } else {
-          *dst = neg_inf_f();
+      {
+        const int n = n0 + tid;                              // my destination vertex (column of the tile)
+        const int ii_hi = min(min(kBI, O - i0), n - i0);     // rows with ir < O and k = n - ir - 1 >= 0
+        const int ii_lo = max(0, n - Tl - i0);               // ... and k < Tl
+        const bool col_on = n < O;
+        float *dst = cs + tid;
+        const float *src = E + (int64_t)i0 * Tl + (n - i0 - 1);          // row ii: src + ii * (Tl - 1)
+        const uint32_t dst_u = smem_u32(dst);
+#pragma unroll 4
+        for (int ii = 0; ii < kBI; ii++) {
+          if (col_on && ii >= ii_lo && ii < ii_hi) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_u + (uint32_t)(ii * kCsPitch * 4)), "l"(src + (int64_t)ii * (Tl - 1)) : "memory");
+          } else {
+            dst[ii * kCsPitch] = neg_inf_f();
+          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
