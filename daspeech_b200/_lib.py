@@ -44,6 +44,9 @@ SIGNATURES = {
     "dagb200_dag_posterior": (_int, [_vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "dagb200_glat_force_emit": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
     "dagb200_glat_alignment": (_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _vp]),
+    "dagb200_decode_lookahead": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _i64, _int, _int, _int, _vp, _vp, _vp, _vp]),
+    "dagb200_decode_viterbi_finish": (_int, [_vp, _vp, _vp, _vp, ctypes.c_float, _i64, _int, _int, _int, _int, _vp, _vp, _vp,
+                                             _vp, _vp]),
     "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "dagb200_dag_best_alignment": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int,
                                           _vp, _sz, _vp, _vp]),

@@ -219,7 +219,7 @@ class _DagKernel:
         return grad_match_all, grad_links
 
     def dag_best_alignment(self, match_all, links, output_length, target_length, config,
-                           want_alpha=True) -> Tuple[Tensor, Tensor]:
+                           want_alpha=True, track_status=True) -> Tuple[Tensor, Tensor]:
         bsz, tarlen, prelen, translen = self._check_lattice(match_all, links, output_length, target_length)
         match_all = match_all.contiguous()
         links = links.contiguous()
@@ -239,7 +239,7 @@ class _DagKernel:
                                                      _DTYPE_CODE[match_all.dtype], bsz, tarlen, prelen, translen,
                                                      int(config), _ptr(workspace), nbytes, _ptr(status), _stream())
         _lib.check(rc, "dag_best_alignment")
-        if bsz:
+        if bsz and track_status:
             self._track_status("dag_best_alignment", status)
         return alpha, path
 

@@ -176,6 +176,28 @@ int dagb200_glat_alignment(const int32_t *path, const int64_t *tgt_tokens, int64
                            const int64_t *pred_tokens, unsigned char *matchmask, int64_t *oracle, int64_t *path64,
                            unsigned char *align_mask, int64_t *same_num, int B, int M, int L, void *stream);
 
+/* Next row: inference decoding over the DAG, replacing the Python walks over `.tolist()`-ed
+ * back-pointers of models/s2s_conformer_dag_fastspeech2.py:211-304.
+ *   vertex_logit [B][L] f32  = max_y log P(y | v_j)   (:216 unreduced_logits)
+ *   vertex_token [B][L] i64  = argmax_y               (:216 unreduced_tokens)
+ *   links        [B][L][T]   banded transitions (the model's extract_links output)
+ * Outputs: out_tokens int64 [B][L] (pad-filled), out_vertices int32 [B][L] (vertex of every emitted feature, -1 fill),
+ * out_lengths int32 [B][2] = (number of tokens, number of features).
+ * decode_lookahead: strategies "greedy" (beta = 0) and "lookahead" (:218-244); tokens start with the token of vertex 0
+ * (<bos>), which carries no feature.
+ * decode_viterbi_finish: strategies "viterbi" / "jointviterbi" (:245-304) AFTER the max-plus recurrence, which is the
+ * lattice of dagb200_dag_best_alignment run on a length-independent emission plane (daspeech_b200/decode.py):
+ * lattice [B][S+1][L] with row s+1 = the reference's scores[s], S = max_length; end transition, length penalty
+ * (s+1)^viterbibeta, first-maximum length, backtrace (smallest source vertex on ties, as torch.max) and token
+ * de-duplication.  path_scratch: int32 [B][S].                                                                        */
+int dagb200_decode_lookahead(const float *links, const float *vertex_logit, const int64_t *vertex_token,
+                             const int64_t *output_length, float beta, int64_t pad, int B, int L, int T,
+                             int64_t *out_tokens, int32_t *out_vertices, int32_t *out_lengths, void *stream);
+int dagb200_decode_viterbi_finish(const float *lattice, const float *links, const int64_t *vertex_token,
+                                  const int64_t *output_length, float viterbibeta, int64_t pad, int B, int S, int L, int T,
+                                  int64_t *out_tokens, int32_t *out_vertices, int32_t *out_lengths, int32_t *path_scratch,
+                                  void *stream);
+
 #ifdef __cplusplus
 }
 #endif
