@@ -12,11 +12,12 @@ inputs resident in HBM.  A DP cell is one (b, t, j) of the padded B x M x L latt
 The step's working set (1.27 GB algorithmic) is ~10x the 126 MB L2, so no explicit L2 flush is needed.
 
 Multi-GPU (torchrun, one rank per GPU): utterances are sharded (B per GPU, weak scaling), no collective inside the
-DP; every step additionally carries the trainer's gradient exchange -- ONE NCCL all-reduce of a 300 MB fp32 buffer
-pre-divided by the world size (fairseq legacy_distributed_data_parallel.py:76-165), issued on a side stream right
-after the backward kernels so that it overlaps the next step's kernels (at most one exchange in flight; the step
-that follows waits for it before starting its own).  `collective` reports its stand-alone duration and the step
-time with the exchange fully exposed; `parts.no_collective` keeps the replica-only number.
+DP; every step additionally carries the trainer's gradient exchange -- the mean over ranks of ONE 300 MB fp32 buffer
+(fairseq legacy_distributed_data_parallel.py:76-165), issued on a side stream right after the backward kernels so that
+it overlaps the next step's kernels (at most one exchange in flight; the step that follows waits for it before
+starting its own).  The exchange runs on the copy engines over NVLink peer memory (dagb200_grad_exchange; NCCL with
+DAGB200_EXCHANGE=nccl).  `collective` reports its stand-alone duration, the step time with the exchange fully exposed
+and the same step with NCCL's all-reduce instead; `parts.no_collective` keeps the replica-only number.
 
 Prints ONE JSON line (rank 0).  Extra objects: roofline (dominant kernel, HBM bound, measured peak from
 MEASURED_PEAKS.json, plus the tensor-core roofline of the same kernel), cpu_baseline (CPU oracle = C port of the
@@ -318,7 +319,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the communicator's kernels run on a high-priority stream with a bounded number of thread blocks: the
+        # exchange is NVLink-bound, not SM-bound, and every block it holds is one the lattice kernels do not get
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=os.environ.get("DAGB200_NCCL_PRIO", "1") == "1")
+        ctas = int(os.environ.get("DAGB200_NCCL_CTAS", "0"))
+        if ctas > 0:
+            opts.config.max_ctas = ctas
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     B, L, M, V = args.batch, args.prelen, args.tarlen, args.vocab
     T = args.translen or (L - 1)
     K, W = args.steps, max(args.warmup, 3)
@@ -333,23 +340,45 @@ def main():
         torch.cuda.synchronize()
 
     # the trainer's gradient exchange (N > 1 only): one flat fp32 buffer, pre-divided, all-reduced on a side stream
-    from daspeech_b200.dist import FlatGradAllReduce
-    exchange = FlatGradAllReduce(int(args.grad_mb * 1e6 / 4), torch.float32, dev) if world > 1 else None
+    from daspeech_b200.dist import FlatGradAllReduce, PeerGradExchange
+    # the step's gradient exchange: copy engines over NVLink peer memory (default) or NCCL (DAGB200_EXCHANGE=nccl);
+    # the other one is timed after the main region for comparison
+    grad_numel = int(args.grad_mb * 1e6 / 4)
+    exchange_kind = os.environ.get("DAGB200_EXCHANGE", "peer")
+    exchange = exchange_nccl = None
+    if world > 1:
+        exchange_nccl = FlatGradAllReduce(grad_numel, torch.float32, dev)
+        exchange = PeerGradExchange(grad_numel, dev) if exchange_kind == "peer" else exchange_nccl
 
     def step():
         alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
         gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
         return alpha, beta, gm, gl
 
-    def run_steps(n, overlap=True, with_exchange=True):
+    trace = [] if os.environ.get("DAGB200_BENCH_TRACE") else None
+
+    def run_steps(n, overlap=True, with_exchange=True, exchange=exchange):
         """n steps; with the exchange of step i overlapping the kernels of step i+1 (overlap) or fully exposed."""
         out = None
         for _ in range(n):
+            if trace is not None:
+                tr = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                trace.append(tr)
+                tr[0].record()
             alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
+            if trace is not None:
+                tr[1].record()
             gm, gl = k.dag_loss_backward(go, alpha, beta, match, links, olen, tlen, 2, 2)
+            if trace is not None:
+                tr[2].record()
             if exchange is not None and with_exchange:
                 exchange.finish()          # the previous step's exchange (a no-op the first time)
+                if trace is not None:
+                    exchange.side.wait_stream(torch.cuda.current_stream())
+                    tr[3].record(exchange.side)
                 exchange.start()           # this step's gradients: side stream, after the backward kernels
+                if trace is not None:
+                    tr[4].record(exchange.side)
                 if not overlap:
                     exchange.finish()
             out = (alpha, beta, gm, gl)
@@ -376,9 +405,19 @@ def main():
     barrier()
     # ---- timed region: exactly K steps -------------------------------------------------------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    if trace is not None:
+        del trace[:]
     ev[0].record()
     alpha, beta, gm, gl = run_steps(K)
     ev[1].record()
+    if trace is not None:
+        torch.cuda.synchronize()
+        rel = lambda t: ev[0].elapsed_time(t)
+        print("rank %d (fwd start, fwd ms, bwd ms | exchange start, ms): %s | end %.3f" % (
+            rank, "  ".join("%.2f %.2f %.2f | %.2f %.2f" % (rel(t[0]), rel(t[1]) - rel(t[0]), rel(t[2]) - rel(t[1]),
+                                                          rel(t[3]), rel(t[4]) - rel(t[3])) for t in trace),
+            rel(ev[1])), file=sys.stderr, flush=True)
+        trace = None
     # The K steps are now queued on the stream (the host enqueues a step in < 0.1 ms, the GPU needs ~1 ms for it).
     # Clocks / throttle reasons are sampled while the GPU works through them: NVML queries take the driver lock, so
     # sampling WHILE launching would stall the launches and show up as idle gaps between kernels.
@@ -411,18 +450,39 @@ def main():
         exposed_ms = timed(lambda n: run_steps(n, overlap=False), kc)
         replica_ms = timed(lambda n: run_steps(n, with_exchange=False), kc)
 
-        def only_exchange(n):
+        def only_exchange(n, ex=exchange):
             for _ in range(n):
-                exchange.start()
-                exchange.finish()
+                ex.start()
+                ex.finish()
         only_exchange(2)
         ar_ms = timed(only_exchange, kc)
+        phases = None
+        if hasattr(exchange, "phases_ms"):
+            exchange.phases_ms()
+            only_exchange(2)
+            phases = dict(zip(("push_scatter", "barrier_b", "reduce", "push_gather", "barrier_c"),
+                              exchange.phases_ms()))
         nbytes = exchange.buffer.numel() * 4
-        collective = {"kind": "nccl all_reduce(sum) of one flat fp32 gradient buffer, pre-divided by the world size",
-                      "bytes": nbytes, "collective_ms": ar_ms,
-                      "busbw_gbs": nbytes * 2 * (world - 1) / world / (ar_ms * 1e-3) / 1e9,
+        busbw = lambda ms: nbytes * 2 * (world - 1) / world / (ms * 1e-3) / 1e9
+        kinds = {"peer": "mean over ranks of one flat fp32 gradient buffer: reduce-scatter + all-gather as peer-to-peer "
+                         "copy-engine transfers over NVLink, one short reduce kernel, flag barriers "
+                         "(dagb200_grad_exchange, daspeech_b200/csrc/xchg.cu)",
+                 "nccl": "nccl all_reduce (pre-multiplied sum) of one flat fp32 gradient buffer"}
+        collective = {"kind": kinds.get(exchange_kind, exchange_kind), "bytes": nbytes, "collective_ms": ar_ms,
+                      "busbw_gbs": busbw(ar_ms),
                       "step_ms_overlapped": ms_per_step, "step_ms_exposed": exposed_ms, "step_ms_no_collective": replica_ms,
                       "reference": "fairseq legacy_distributed_data_parallel.py:76-165 via trainer.py:928"}
+        if phases:
+            collective["phases_ms_standalone"] = phases
+        if exchange is not exchange_nccl:
+            run_steps(3, exchange=exchange_nccl)
+            nccl_ms = timed(lambda n: run_steps(n, exchange=exchange_nccl), kc)
+            only_exchange(2, exchange_nccl)
+            nccl_ar = timed(lambda n: only_exchange(n, exchange_nccl), kc)
+            collective["nccl_comparison"] = {"step_ms_overlapped": nccl_ms, "collective_ms": nccl_ar,
+                                             "busbw_gbs": busbw(nccl_ar)}
+            if hasattr(exchange, "timed_out_epoch"):
+                collective["barrier_timeouts"] = exchange.timed_out_epoch()
 
     # ---- per-kernel durations: CUDA events recorded by the library on the launch stream around each of its
     # kernels (dagb200_set_profile), averaged over a few extra steps right after the timed region -----------
@@ -612,7 +672,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, T),
                 "utt_per_sec": B * world / (ms_per_step * 1e-3), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": 5 * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
+                "gpu_launches": (5 + (3 if world > 1 and exchange_kind == "peer" else 0)) * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
         if collective is not None:
             line["collective"] = collective
             parts["no_collective"] = {"ms_per_step": collective["step_ms_no_collective"],

@@ -50,6 +50,17 @@ SIGNATURES = {
     "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "dagb200_dag_best_alignment": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int,
                                           _vp, _sz, _vp, _vp]),
+    "dagb200_peer_alloc": (_int, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
+    "dagb200_peer_free": (_int, [_vp]),
+    "dagb200_peer_export": (_int, [_vp, _vp]),
+    "dagb200_peer_open": (_int, [_vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "dagb200_peer_close": (_int, [_vp]),
+    "dagb200_grad_exchange_slice": (_sz, [_sz, _int]),
+    "dagb200_grad_exchange_create": (_int, [_vp, _vp, _vp, _sz, _int, _int, ctypes.POINTER(ctypes.c_void_p)]),
+    "dagb200_grad_exchange": (_int, [_vp, _vp]),
+    "dagb200_grad_exchange_status": (_int, [_vp, ctypes.POINTER(_int)]),
+    "dagb200_grad_exchange_phases": (_int, [_vp, _vp]),
+    "dagb200_grad_exchange_destroy": (_int, [_vp]),
 }
 
 

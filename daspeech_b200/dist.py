@@ -80,8 +80,11 @@ class FlatGradAllReduce:
     def __init__(self, numel: int, dtype=torch.float32, device=None):
         self.buffer = torch.zeros(numel, dtype=dtype, device=device)
         self.cuda = self.buffer.is_cuda
-        self.side = torch.cuda.Stream(device=self.buffer.device) if self.cuda else None
+        # highest priority: the exchange kernel's few thread blocks are placed as soon as any block of the compute
+        # stream retires, instead of waiting behind the whole grid of the kernel that happens to be running
+        self.side = torch.cuda.Stream(device=self.buffer.device, priority=-1) if self.cuda else None
         self._done = None
+        self._premul = None
 
     def start(self):
         _, ws = world()
@@ -93,8 +96,11 @@ class FlatGradAllReduce:
         self.side.wait_stream(torch.cuda.current_stream(self.buffer.device))
         with torch.cuda.stream(self.side):
             if ws > 1:
-                self.buffer.div_(ws)
-                dist.all_reduce(self.buffer)
+                # the division by the world size rides inside the collective (NCCL pre-multiplied sum): no extra
+                # read+write pass over the buffer
+                if self._premul is None:
+                    self._premul = dist._make_nccl_premul_sum(1.0 / ws)
+                dist.all_reduce(self.buffer, op=self._premul)
             self._done = torch.cuda.Event()
             self._done.record(self.side)
 
@@ -103,3 +109,127 @@ class FlatGradAllReduce:
             torch.cuda.current_stream(self.buffer.device).wait_event(self._done)
             self._done = None
         return self.buffer
+
+
+class _RawDeviceArray:
+    """A cudaMalloc allocation seen through __cuda_array_interface__ (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr: int, numel: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerGradExchange:
+    """The same exchange as `FlatGradAllReduce` (one flat fp32 gradient buffer -> mean over ranks, fairseq
+    legacy_distributed_data_parallel.py:76-165 via trainer.py:928), moved by the COPY ENGINES over NVLink peer memory:
+    reduce-scatter and all-gather as peer-to-peer cudaMemcpyAsync pushes between IPC-mapped buffers, one short kernel
+    that sums the rank's own 1/world slice, two flag barriers (daspeech_b200/csrc/xchg.cu, C ABI dagb200_grad_exchange*).
+    No thread block is held for the duration of the transfer, so the lattice kernels of the next step keep the SMs.
+
+    One process per GPU of ONE node; the default process group (any backend) carries the 64-byte IPC handles once, at
+    construction.  `start()` / `finish()` as in FlatGradAllReduce.  All ranks end with bit-identical buffers."""
+
+    def __init__(self, numel: int, device=None, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = world()
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.numel = (int(numel) + 3) // 4 * 4
+        self._ctypes = ctypes
+        self._owned, self._opened, self._handle = [], [], ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            slice_ = self.lib.dagb200_grad_exchange_slice(self.numel, self.world)
+            buf = self._alloc(self.numel * 4)
+            flags = self._alloc(32 * 4)
+            staging = self._alloc(max(1, (self.world - 1) * slice_) * 4)
+            bufs, flagss, stagings = [buf], [flags], [staging]
+            if self.world > 1:
+                mine = torch.tensor(list(self._export(buf) + self._export(flags) + self._export(staging)), dtype=torch.uint8)
+                if dist.get_backend(group) == "nccl":
+                    mine = mine.to(self.device)
+                every = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(every, mine, group=group)
+                bufs, flagss, stagings = [], [], []
+                for p, h in enumerate(every):
+                    if p == self.rank:
+                        bufs.append(buf)
+                        flagss.append(flags)
+                        stagings.append(staging)
+                        continue
+                    raw = bytes(h.cpu().tolist())
+                    bufs.append(self._open(raw[:64]))
+                    flagss.append(self._open(raw[64:128]))
+                    stagings.append(self._open(raw[128:]))
+            arr = ctypes.c_void_p * self.world
+            _lib.check(self.lib.dagb200_grad_exchange_create(arr(*bufs), arr(*flagss), arr(*stagings), self.numel, self.rank,
+                                                             self.world, ctypes.byref(self._handle)),
+                       "grad_exchange_create")
+        self.buffer = torch.as_tensor(_RawDeviceArray(buf, self.numel, "<f4"), device=self.device)
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._done = None
+        if self.world > 1:
+            dist.barrier(group=group)       # every rank has opened every handle before anybody's first exchange
+
+    def _alloc(self, nbytes):
+        from . import _lib
+        p = self._ctypes.c_void_p()
+        _lib.check(self.lib.dagb200_peer_alloc(nbytes, self._ctypes.byref(p)), "peer_alloc")
+        self._owned.append(p.value)
+        return p.value
+
+    def _export(self, ptr):
+        from . import _lib
+        h = (self._ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.dagb200_peer_export(ptr, h), "peer_export")
+        return tuple(h)
+
+    def _open(self, raw):
+        from . import _lib
+        h = (self._ctypes.c_ubyte * 64)(*raw)
+        p = self._ctypes.c_void_p()
+        _lib.check(self.lib.dagb200_peer_open(h, self._ctypes.byref(p)), "peer_open")
+        self._opened.append(p.value)
+        return p.value
+
+    def start(self):
+        from . import _lib
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.dagb200_grad_exchange(self._handle, self.side.cuda_stream), "grad_exchange")
+        self._done = torch.cuda.Event()
+        self._done.record(self.side)
+
+    def finish(self):
+        if self._done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done)
+            self._done = None
+        return self.buffer
+
+    def phases_ms(self):
+        """Durations of push, barrier, reduce, push, barrier of the most recent exchange (the first call only switches
+        the recording on)."""
+        from . import _lib
+        ms = (self._ctypes.c_float * 5)()
+        _lib.check(self.lib.dagb200_grad_exchange_phases(self._handle, ms), "grad_exchange_phases")
+        return list(ms)
+
+    def timed_out_epoch(self) -> int:
+        """0 when every barrier so far completed; synchronises the device (diagnostic)."""
+        from . import _lib
+        e = self._ctypes.c_int(0)
+        _lib.check(self.lib.dagb200_grad_exchange_status(self._handle, self._ctypes.byref(e)), "grad_exchange_status")
+        return e.value
+
+    def close(self):
+        if self._handle:
+            torch.cuda.synchronize(self.device)
+            self.lib.dagb200_grad_exchange_destroy(self._handle)
+            self._handle = self._ctypes.c_void_p()
+            self.buffer = None
+            for p in self._opened:
+                self.lib.dagb200_peer_close(p)
+            if self.world > 1:
+                dist.barrier()              # nobody frees an allocation a peer still has mapped
+            for p in self._owned:
+                self.lib.dagb200_peer_free(p)
+            self._opened, self._owned = [], []

@@ -198,6 +198,32 @@ int dagb200_decode_viterbi_finish(const float *lattice, const float *links, cons
                                   int64_t *out_tokens, int32_t *out_vertices, int32_t *out_lengths, int32_t *path_scratch,
                                   void *stream);
 
+/* ---- Data-parallel gradient exchange over NVLink peer memory (daspeech_b200/csrc/xchg.cu) ---------------------------
+ * Replaces fairseq legacy_distributed_data_parallel.py:76-165 (one flat gradient buffer, divided by the world size,
+ * all-reduced) as called from trainer.py:928.  One process per GPU of one node.  The bytes move on the copy engines
+ * (peer-to-peer cudaMemcpyAsync), the sum of each 1/world slice runs as one short kernel on the rank that owns the
+ * slice; all ranks end with bit-identical buffers.
+ *   peer_alloc/free   : a cudaMalloc allocation (zero-filled) that can be exported; the library owns nothing else.
+ *   peer_export/open  : 64-byte cudaIpcMemHandle of an allocation / map a peer's allocation into this process.
+ *   grad_exchange_create(bufs, flags, stagings, numel, rank, world, &h), entry [rank] local, the others opened:
+ *       bufs[p]  float[numel] of rank p, numel a multiple of 4;  flags[p] int32[32] of rank p, zero-initialised;
+ *       stagings[p] float[(world-1) * grad_exchange_slice(numel, world)] of rank p.
+ *   grad_exchange(h, stream): enqueue one exchange; stream-ordered, never blocks the host.
+ *   grad_exchange_status(h, &epoch): 0, or the barrier epoch at which a peer failed to arrive within ~4 s
+ *       (synchronises the device; diagnostic).                                                                        */
+int dagb200_peer_alloc(size_t bytes, void **ptr);
+int dagb200_peer_free(void *ptr);
+int dagb200_peer_export(void *ptr, void *handle64);
+int dagb200_peer_open(const void *handle64, void **ptr);
+int dagb200_peer_close(void *ptr);
+size_t dagb200_grad_exchange_slice(size_t numel, int world);
+int dagb200_grad_exchange_create(void *const *bufs, void *const *flags, void *const *stagings, size_t numel, int rank,
+                                 int world, void **handle);
+int dagb200_grad_exchange(void *handle, void *stream);
+int dagb200_grad_exchange_status(void *handle, int *timed_out_epoch);
+int dagb200_grad_exchange_phases(void *handle, float *ms5);   /* measurement aid: push, barrier, reduce, push, barrier */
+int dagb200_grad_exchange_destroy(void *handle);
+
 #ifdef __cplusplus
 }
 #endif
