@@ -340,15 +340,21 @@ def main():
         torch.cuda.synchronize()
 
     # the trainer's gradient exchange (N > 1 only): one flat fp32 buffer, pre-divided, all-reduced on a side stream
-    from daspeech_b200.dist import FlatGradAllReduce, PeerGradExchange
-    # the step's gradient exchange: copy engines over NVLink peer memory (default) or NCCL (DAGB200_EXCHANGE=nccl);
-    # the other one is timed after the main region for comparison
+    from daspeech_b200.dist import FlatGradAllReduce, make_grad_exchange
+    # the step's gradient exchange (DAGB200_EXCHANGE): "nvls" = reduced inside the NVSwitch by this library's multimem
+    # kernel, "peer" = copy engines over NVLink peer memory, "nccl"; default "auto" = the first that can be set up on
+    # this box.  NCCL's all-reduce is timed after the main region for comparison.
     grad_numel = int(args.grad_mb * 1e6 / 4)
-    exchange_kind = os.environ.get("DAGB200_EXCHANGE", "peer")
+    exchange_kind = os.environ.get("DAGB200_EXCHANGE", "auto")
     exchange = exchange_nccl = None
     if world > 1:
         exchange_nccl = FlatGradAllReduce(grad_numel, torch.float32, dev)
-        exchange = PeerGradExchange(grad_numel, dev) if exchange_kind == "peer" else exchange_nccl
+        if exchange_kind == "nccl":
+            exchange = exchange_nccl
+        else:
+            exchange, exchange_kind = make_grad_exchange(grad_numel, dev, exchange_kind)
+            if exchange_kind == "nccl":
+                exchange = exchange_nccl
 
     def step():
         alpha, beta = k.dag_loss(match, links, olen, tlen, True, 1)
@@ -464,7 +470,10 @@ def main():
                               exchange.phases_ms()))
         nbytes = exchange.buffer.numel() * 4
         busbw = lambda ms: nbytes * 2 * (world - 1) / world / (ms * 1e-3) / 1e9
-        kinds = {"peer": "mean over ranks of one flat fp32 gradient buffer: reduce-scatter + all-gather as peer-to-peer "
+        kinds = {"nvls": "mean over ranks of one flat fp32 gradient buffer reduced inside the NVSwitch: multimem.ld_reduce + "
+                         "multimem.st on a multicast mapping, one kernel of 8 thread blocks per rank "
+                         "(dagb200_grad_exchange_nvls, daspeech_b200/csrc/xchg.cu); mapping and barriers: torch symmetric memory",
+                 "peer": "mean over ranks of one flat fp32 gradient buffer: reduce-scatter + all-gather as peer-to-peer "
                          "copy-engine transfers over NVLink, one short reduce kernel, flag barriers "
                          "(dagb200_grad_exchange, daspeech_b200/csrc/xchg.cu)",
                  "nccl": "nccl all_reduce (pre-multiplied sum) of one flat fp32 gradient buffer"}
@@ -672,7 +681,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, T),
                 "utt_per_sec": B * world / (ms_per_step * 1e-3), "clocks": clk.summary(), "e2e": e2e,
-                "gpu_launches": (5 + (3 if world > 1 and exchange_kind == "peer" else 0)) * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
+                "gpu_launches": (5 + ({"peer": 3, "nvls": 1}.get(exchange_kind, 0) if world > 1 else 0)) * K, "roofline": roofline, "loss_check": loss_check, "parts": parts}
         if collective is not None:
             line["collective"] = collective
             parts["no_collective"] = {"ms_per_step": collective["step_ms_no_collective"],

@@ -61,6 +61,7 @@ SIGNATURES = {
     "dagb200_grad_exchange_status": (_int, [_vp, ctypes.POINTER(_int)]),
     "dagb200_grad_exchange_phases": (_int, [_vp, _vp]),
     "dagb200_grad_exchange_destroy": (_int, [_vp]),
+    "dagb200_grad_exchange_nvls": (_int, [_vp, _sz, _int, _int, _int, _vp]),
 }
 
 

@@ -233,3 +233,70 @@ class PeerGradExchange:
             for p in self._owned:
                 self.lib.dagb200_peer_free(p)
             self._opened, self._owned = [], []
+
+
+class NvlsGradExchange:
+    """The same exchange reduced INSIDE the NVSwitch: the buffer lives in symmetric memory bound to a multicast object
+    (`torch.distributed._symmetric_memory` does the mapping and provides the stream-ordered barriers -- plumbing), and one
+    small kernel of this library (`dagb200_grad_exchange_nvls`, csrc/xchg.cu: `multimem.ld_reduce` + `multimem.st`)
+    turns every rank's 1/world slice into the mean over ranks in all copies.  A GPU sends and receives 300 MB per
+    exchange whatever the world size (point-to-point reduce-scatter + all-gather: 525 MB each way at 8 GPUs), from
+    8 thread blocks (measured at 8 GPUs: 0.70 ms alone with 8 or 16 blocks, 0.85 with 4, 1.57 with 2; step with the
+    exchange overlapped 1.29 ms with 8 blocks, 1.64 with 16), so the 128 recurrence CTAs of the next step stay resident.
+    Raises RuntimeError when the box has no multicast support; callers fall back to PeerGradExchange."""
+
+    def __init__(self, numel: int, device=None, group=None, ctas: int = 8):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = world()
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.numel = (int(numel) + 3) // 4 * 4
+        import os
+        self.ctas = int(os.environ.get("DAGB200_NVLS_CTAS", ctas))
+        self.group = group if group is not None else dist.group.WORLD
+        self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        self.mc = int(self.handle.multicast_ptr)
+        if not self.mc:
+            raise RuntimeError("no multicast (NVLink SHARP) mapping for symmetric memory on this box")
+        self.buffer.zero_()
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._done = None
+
+    def start(self):
+        from . import _lib
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            self.handle.barrier(channel=0)          # every rank's gradients are in its buffer
+            _lib.check(self.lib.dagb200_grad_exchange_nvls(self.mc, self.numel, self.rank, self.world, self.ctas,
+                                                           self.side.cuda_stream), "grad_exchange_nvls")
+            self.handle.barrier(channel=1)          # every slice has landed in every copy
+            self._done = torch.cuda.Event()
+            self._done.record(self.side)
+
+    def finish(self):
+        if self._done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done)
+            self._done = None
+        return self.buffer
+
+
+def make_grad_exchange(numel: int, device, kind: str = "auto"):
+    """The gradient exchange for this box: "nvls" (in-switch), "peer" (copy engines), "nccl", or "auto" = the first of
+    those that can be set up.  Returns (exchange, kind)."""
+    _, ws = world()
+    order = {"auto": ("nvls", "peer", "nccl")}.get(kind, (kind,))
+    last = None
+    for k in order:
+        try:
+            if k == "nvls":
+                if ws < 2:
+                    raise RuntimeError("single rank")
+                return NvlsGradExchange(numel, device), k
+            if k == "peer":
+                return PeerGradExchange(numel, device), k
+            return FlatGradAllReduce(numel, torch.float32, device), "nccl"
+        except Exception as e:   # noqa: BLE001 -- set-up failures select the next mechanism
+            last = e
+    raise RuntimeError("no gradient exchange could be set up: %r" % (last,))

@@ -223,6 +223,10 @@ int dagb200_grad_exchange(void *handle, void *stream);
 int dagb200_grad_exchange_status(void *handle, int *timed_out_epoch);
 int dagb200_grad_exchange_phases(void *handle, float *ms5);   /* measurement aid: push, barrier, reduce, push, barrier */
 int dagb200_grad_exchange_destroy(void *handle);
+/* In-switch form: mc = MULTICAST address of a buffer every rank has bound to the same multicast object (NVLink SHARP;
+ * the caller maps it and synchronises the ranks before and after).  One kernel of `ctas` thread blocks: this rank's 1/world
+ * slice of mc[0 .. numel) becomes (sum over ranks) / world in every rank's copy (multimem.ld_reduce / multimem.st). */
+int dagb200_grad_exchange_nvls(void *mc, size_t numel, int rank, int world, int ctas, void *stream);
 
 #ifdef __cplusplus
 }

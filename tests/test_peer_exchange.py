@@ -61,3 +61,47 @@ def test_peer_exchange_is_the_mean_over_ranks(tmp_path, numel):
     assert r["timed_out"] == 0
     assert r["identical"], "ranks must end with bit-identical buffers"
     assert r["worst"] < 1e-6
+
+
+def _nvls_worker(rank, ws, port, numel, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev)
+    from daspeech_b200.dist import NvlsGradExchange
+    res = {"skipped": None}
+    try:
+        ex = NvlsGradExchange(numel, device=dev)
+    except Exception as e:   # no multicast support on this box
+        res["skipped"] = repr(e)[:200]
+        ex = None
+    if ex is not None:
+        worst, identical = 0.0, True
+        for it in range(4):
+            ex.buffer[:numel].copy_(_fill(numel, rank, it))
+            ex.start()
+            got = ex.finish()[:numel].clone()
+            want = sum(_fill(numel, r, it).double() for r in range(ws)) / ws
+            worst = max(worst, float((got.double().cpu() - want).abs().max() / want.abs().max()))
+            every = [torch.empty_like(got) for _ in range(ws)]
+            dist.all_gather(every, got)
+            identical = identical and all(torch.equal(every[0], e) for e in every)
+        res.update(worst=worst, identical=identical)
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("numel", [1_000_004, 4096])
+def test_nvls_exchange_is_the_mean_over_ranks(tmp_path, numel):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("the in-switch exchange needs two GPUs of one NVSwitch domain")
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_nvls_worker, args=(2, _free_port(), numel, out), nprocs=2, join=True)
+    r = torch.load(out)
+    if r["skipped"]:
+        pytest.skip(r["skipped"])
+    assert r["identical"], "ranks must end with bit-identical buffers"
+    assert r["worst"] < 1e-6

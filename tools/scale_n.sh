@@ -11,7 +11,7 @@ try:
     print("$tag", "N=%d" % d["n_gpus"], "step %.3f" % d["ms_per_step"], "exposed %.3f" % c["step_ms_exposed"],
           "none %.3f" % c["step_ms_no_collective"], "alone %.3f" % c["collective_ms"],
           {k: round(v, 3) for k, v in (c.get("phases_ms_standalone") or {}).items()},
-          "nccl %.3f" % c["nccl_comparison"]["step_ms_overlapped"] if "nccl_comparison" in c else "", "timeouts", c.get("barrier_timeouts"))
+          "nccl %.3f" % c["nccl_comparison"]["step_ms_overlapped"] if "nccl_comparison" in c else "", c["kind"][:40], "timeouts", c.get("barrier_timeouts"))
 except Exception as e:
     print("$tag failed", e); print(open("gpurun_out/sc_$tag.err").read()[-1500:])
 PY
