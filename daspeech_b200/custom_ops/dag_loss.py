@@ -81,12 +81,15 @@ class _DagKernel:
         self._pending = []      # (what, pinned host copy of the per-sample status, event) of earlier calls
         self._pinned = None
         self._free = []
+        self.track = True       # False: status words are produced but not copied back (CUDA-graph capture, graphs.py)
 
     # ---- per-sample device status (the reference's CUDA_KERNEL_ASSERTs, dag_loss.cu:68-69, dag_best_alignment.cu:67-70,118)
     # The status words are always produced (B int32).  DAGB200_DEBUG=1 checks them synchronously and raises; otherwise
     # they are copied to pinned host memory without a sync and inspected at the next operator call (or by
     # `check_pending_status()`), where a violation becomes a RuntimeWarning naming the sample.
     def _track_status(self, what, status):
+        if not self.track:
+            return
         if _DEBUG:
             _check_status(status)
             return

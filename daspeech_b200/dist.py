@@ -245,7 +245,7 @@ class NvlsGradExchange:
     exchange overlapped 1.29 ms with 8 blocks, 1.64 with 16), so the 128 recurrence CTAs of the next step stay resident.
     Raises RuntimeError when the box has no multicast support; callers fall back to PeerGradExchange."""
 
-    def __init__(self, numel: int, device=None, group=None, ctas: int = 8):
+    def __init__(self, numel: int, device=None, group=None, ctas: int = 0):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self.lib = _lib.load()
@@ -253,7 +253,11 @@ class NvlsGradExchange:
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
         self.numel = (int(numel) + 3) // 4 * 4
         import os
-        self.ctas = int(os.environ.get("DAGB200_NVLS_CTAS", ctas))
+        # thread blocks of the exchange kernel: enough to keep the switch busy with this rank's slice (37.5 MB at 8 ranks:
+        # 8 blocks run at full speed; 150 MB at 2 ranks: 8 blocks take 1.5 ms, 16 take 0.84), as few as possible otherwise
+        slice_mb = self.numel * 4 / self.world / 1e6
+        auto = max(8, min(24, int(round(slice_mb / 4.7))))
+        self.ctas = int(os.environ.get("DAGB200_NVLS_CTAS", ctas or auto))
         self.group = group if group is not None else dist.group.WORLD
         self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=self.device)
         self.handle = symm_mem.rendezvous(self.buffer, self.group)
@@ -286,7 +290,9 @@ def make_grad_exchange(numel: int, device, kind: str = "auto"):
     """The gradient exchange for this box: "nvls" (in-switch), "peer" (copy engines), "nccl", or "auto" = the first of
     those that can be set up.  Returns (exchange, kind)."""
     _, ws = world()
-    order = {"auto": ("nvls", "peer", "nccl")}.get(kind, (kind,))
+    # two ranks: the copy engines move the 150 MB slices without holding SMs (0.69 ms) and the in-switch form has
+    # nothing to save (it moves more bytes than point-to-point at N = 2); from four ranks on the switch reduces
+    order = {"auto": ("peer", "nvls", "nccl") if ws <= 2 else ("nvls", "peer", "nccl")}.get(kind, (kind,))
     last = None
     for k in order:
         try:

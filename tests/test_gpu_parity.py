@@ -818,3 +818,22 @@ def test_full_size_c2_properties():
         assert elem_err(mine, truth) <= grad_tol(ref32, truth), (elem_err(mine, truth), elem_err(ref32, truth))
     _, opath, _ = oracle.dag_best_alignment(mm, ll, oo, tt, 1, np.float32)
     assert np.array_equal(path[sub].cpu().numpy(), opath.astype(np.int64))
+
+
+def test_cuda_graph_replay_of_the_step_equals_the_eager_calls():
+    """daspeech_b200.graphs.GraphedDagLossStep: the six kernels of a step captured once and replayed -- same bytes as
+    the eager calls, also after the inputs were rewritten in place."""
+    from daspeech_b200.graphs import GraphedDagLossStep
+    B, L, M, T = 6, 320, 70, 319
+    k = ops.get_dag_kernel()
+    go = torch.rand(B, device=DEV) + 0.5
+    lat = [oracle.make_lattice(B, L, M, T, seed=s, ragged=True) for s in (5, 6)]
+    m, lk, ol, tl = (cu(x) for x in lat[0])
+    step = GraphedDagLossStep(m, lk, ol, tl, go)
+    for match, links, olen, tlen in lat:
+        m.copy_(cu(match)); lk.copy_(cu(links)); ol.copy_(cu(olen)); tl.copy_(cu(tlen))
+        a1, b1, gm1, gl1 = (t.clone() for t in step.replay())
+        a0, b0 = k.dag_loss(m, lk, ol, tl, True, 1)
+        gm0, gl0 = k.dag_loss_backward(go, a0, b0, m, lk, ol, tl, 2, 2)
+        for x, y in ((a1, a0), (b1, b0), (gm1, gm0), (gl1, gl0)):
+            assert torch.equal(x, y)
