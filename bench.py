@@ -368,7 +368,12 @@ def main():
     graphed = None
     if os.environ.get("DAGB200_BENCH_GRAPH", "1") == "1" and trace is None:
         from daspeech_b200.graphs import GraphedDagLossStep
-        graphed = GraphedDagLossStep(match, links, olen, tlen, go)
+        try:
+            graphed = GraphedDagLossStep(match, links, olen, tlen, go)
+        except Exception as e:   # noqa: BLE001 -- a box that cannot capture times the eager calls, and says so
+            print("CUDA graph capture failed (%r): timing the eager operator calls" % (e,), file=sys.stderr)
+            torch.cuda.synchronize()
+            graphed = None
 
     def run_steps(n, overlap=True, with_exchange=True, exchange=exchange):
         """n steps; with the exchange of step i overlapping the kernels of step i+1 (overlap) or fully exposed."""
