@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["cabi.cu", "lsg.cu", "dag_dp.cu", "dag_prep.cu", "dag_dp4.cu", "dag_viterbi3.cu", "dag_grad.cu", "dag_grad4.cu", "dag_posterior.cu", "dag_glat.cu", "dag_decode.cu", "xchg.cu"]
+SOURCES = ["cabi.cu", "lsg.cu", "dag_dp.cu", "dag_prep.cu", "dag_dp4.cu", "dag_viterbi3.cu", "dag_grad.cu", "dag_grad4.cu", "dag_posterior.cu", "dag_glat.cu", "dag_decode.cu", "dag_links.cu", "xchg.cu"]
 OUT = os.path.join(HERE, "libdagb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

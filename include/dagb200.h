@@ -198,6 +198,16 @@ int dagb200_decode_viterbi_finish(const float *lattice, const float *links, cons
                                   int64_t *out_tokens, int32_t *out_vertices, int32_t *out_lengths, int32_t *path_scratch,
                                   void *stream);
 
+/* ---- Transition log-probabilities from the link heads -----------------------------------------
+ * Forward of extract_links + extract_valid_links (DASpeech/models/s2t_conformer_dag.py:171-212, 140-155) for the banded
+ * form (max_transition_length != -1):  links[b][i][k] = logsumexp_c( log_softmax_k( q[b,i,c,:].key[b,i+k+1,c,:] / sqrt(F) )
+ * + log_gates[b,i,c] ), successors j = i+k+1 < output_length[b], -inf elsewhere.
+ *   q, key: fp32 [B][L][H][F] (reshaped outputs of query_linear / key_linear); log_gates: fp32 [B][L][H];
+ *   output_length: int64 [B] (non-pad positions); links: fp32 [B][L][T], every element written.
+ *   F a multiple of 16 in [16, 128], H <= 64.  tcgen05 (bf16 hi/lo split, fp32 accumulate); no [B,L,L,H] temporary. */
+int dagb200_extract_links(const float *q, const float *key, const float *log_gates, const int64_t *output_length,
+                          float *links, int B, int L, int H, int F, int T, void *stream);
+
 /* ---- Data-parallel gradient exchange over NVLink peer memory (daspeech_b200/csrc/xchg.cu) ---------------------------
  * Replaces fairseq legacy_distributed_data_parallel.py:76-165 (one flat gradient buffer, divided by the world size,
  * all-reduced) as called from trainer.py:928.  One process per GPU of one node.  The bytes move on the copy engines
