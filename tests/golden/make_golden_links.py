@@ -1,4 +1,4 @@
-"""Generate tests/golden/links_*.npz by running the UNMODIFIED reference functions `logsumexp`, `extract_valid_links` and
+"""Generate tests/golden/links/links_*.npz by running the UNMODIFIED reference functions `logsumexp`, `extract_valid_links` and
 `extract_links` of /root/reference/DASpeech/models/s2t_conformer_dag.py on CPU.
 
 The model file imports fairseq (absent offline), so the three function definitions are cut out of the file's syntax
@@ -59,7 +59,7 @@ def case(name, B, L, H, Fd, T, lengths, seed):
     fin = torch.isfinite(links)
     (links.masked_fill(~fin, 0.0) * w).sum().backward()
     x = torch.cat([features, link_positional(tokens)], dim=-1)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"),
+    np.savez_compressed(os.path.join(HERE, "links", name + ".npz"),
                         features=features.detach().numpy(), tokens=tokens.numpy(), pos=link_positional(tokens).detach().numpy(),
                         qw=ql.weight.detach().numpy(), qb=ql.bias.detach().numpy(), kw=kl.weight.detach().numpy(),
                         kb=kl.bias.detach().numpy(), gw=gl.weight.detach().numpy(), gb=gl.bias.detach().numpy(),

@@ -10,7 +10,7 @@ import torch
 
 from daspeech_b200 import links as dl
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "links")
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "links_*.npz")))
 
 
