@@ -6,8 +6,9 @@
 //   s[c][k]  = q[b,i,c,:] . key[b,j,c,:] / sqrt(F)                      einsum("bicf,bjcf->bijc") -> [B,L,L,H] fp32 (2.1 GB at C2)
 //   lp[c][k] = s[c][k] - logsumexp_k s[c][k]                             gather of the band, masked log_softmax over successors
 //   links[k] = logsumexp_c (lp[c][k] + log_gates[b,i,c])                 mixture over the heads
-// several [B,L,T,H] temporaries.  Here a CTA owns 128 consecutive vertices of one utterance and never materialises
-// anything but the [B,L,T] result:
+// several [B,L,T,H] temporaries.  Here a CTA owns 128 consecutive vertices of one utterance and nothing is materialised
+// but the [B,L,T] result and [B,H,L] row normalisers (two launches: one CTA per (row tile, head), then one per (row
+// tile, pair of destination blocks)):
 //   pass 1  for every head: S = Q K^T tile by tile (128 x 64, K = F) on the tensor cores -- tcgen05.mma kind::f16 with
 //           both operands split bf16 hi/lo (3 MMAs per k16 step: 2^-16 relative, fp32 accumulate in TMEM) -- and the
 //           online maximum / sum of every row (thread = row = TMEM lane) -> lse[c] per row;
@@ -103,29 +104,46 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// `nrows` vertices starting at `v0` of head c as an MMA operand: [plane hi|lo][k-core][row][8 bf16 along K], scaled
+// `nrows` vertices starting at `v0` of head c as an MMA operand: [plane hi|lo][k-core][row][8 bf16 along K], scaled.
+// Four items (32 bytes each) are requested per thread before the first one is converted: the staging of a tile is one
+// L2 latency, not one per item (the first version converted item by item and spent two thirds of a tile in here).
 __device__ __forceinline__ void stage_operand(unsigned char *dst, const float *__restrict__ src, int v0, int nrows, int L,
                                               int H, int F, int c, float scale) {
+  constexpr int NB = 4;
   const int F8 = F >> 3;
+  const int nitems = nrows * F8;
   const size_t plane = (size_t)F8 * nrows * 16;
-  for (int item = threadIdx.x; item < nrows * F8; item += kThreads) {
-    const int kc = item / nrows, r = item - kc * nrows;     // consecutive threads: consecutive rows (conflict-free stores)
-    const int v = v0 + r;
-    float x[8];
-    if (v < L) {
-      const float4 *p = reinterpret_cast<const float4 *>(src + ((size_t)v * H + c) * F + 8 * kc);
-      const float4 a = __ldg(p), b = __ldg(p + 1);
-      x[0] = a.x * scale; x[1] = a.y * scale; x[2] = a.z * scale; x[3] = a.w * scale;
-      x[4] = b.x * scale; x[5] = b.y * scale; x[6] = b.z * scale; x[7] = b.w * scale;
-    } else {
+  for (int base = threadIdx.x; base < nitems; base += kThreads * NB) {
+    float4 a[NB], b[NB];
 #pragma unroll
-      for (int e = 0; e < 8; e++) x[e] = 0.f;
+    for (int u = 0; u < NB; u++) {
+      const int item = base + u * kThreads;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      b[u] = a[u];
+      if (item < nitems) {
+        const int kc = item / nrows, r = item - kc * nrows;   // consecutive threads: consecutive rows (conflict-free stores)
+        const int v = v0 + r;
+        if (v < L) {
+          const float4 *p = reinterpret_cast<const float4 *>(src + ((size_t)v * H + c) * F + 8 * kc);
+          a[u] = __ldg(p);
+          b[u] = __ldg(p + 1);
+        }
+      }
     }
-    uint4 hi, lo;
-    split8(x, hi, lo);
-    unsigned char *q = dst + ((size_t)kc * nrows + r) * 16;
-    *reinterpret_cast<uint4 *>(q) = hi;
-    *reinterpret_cast<uint4 *>(q + plane) = lo;
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+      const int item = base + u * kThreads;
+      if (item < nitems) {
+        const int kc = item / nrows, r = item - kc * nrows;
+        const float x[8] = {a[u].x * scale, a[u].y * scale, a[u].z * scale, a[u].w * scale,
+                            b[u].x * scale, b[u].y * scale, b[u].z * scale, b[u].w * scale};
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        unsigned char *q = dst + ((size_t)kc * nrows + r) * 16;
+        *reinterpret_cast<uint4 *>(q) = hi;
+        *reinterpret_cast<uint4 *>(q + plane) = lo;
+      }
+    }
   }
 }
 
@@ -146,13 +164,24 @@ __device__ __forceinline__ void issue_tile(uint32_t tmem_d, uint32_t q_u32, uint
   umma_commit(bar);
 }
 
+// MODE 0 (grid: row tile, head, utterance): pass 1 of ONE head -> stats[b][c][i].
+// MODE 1 (grid: row tile x column group, utterance): pass 2 of kGroup destination blocks, all heads -> links.
+// Two launches instead of one CTA per row tile doing everything: the first row tile of an utterance has 16 destination
+// blocks x 8 heads x 2 passes = 256 tiles against 32 for the last one, and the kernel ran as long as its heaviest CTA.
+constexpr int kGroup = 2;
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restrict__ key, const float *__restrict__ log_gates,
-                             const int64_t *__restrict__ olen, float *__restrict__ links, int L, int H, int F, int T) {
+                             const int64_t *__restrict__ olen, float *__restrict__ stats, float *__restrict__ links, int L,
+                             int H, int F, int T, int ngroups) {
   extern __shared__ __align__(128) unsigned char lk_smem[];
-  const int b = blockIdx.y, i0 = blockIdx.x * kRows;
+  const int b = MODE == 0 ? blockIdx.z : blockIdx.y;
+  const int rt = MODE == 0 ? blockIdx.x : blockIdx.x / ngroups;
+  const int grp = MODE == 0 ? 0 : blockIdx.x % ngroups;
+  const int i0 = rt * kRows;
   const int O = min((int)olen[b], L);
   if (i0 >= O - 1) return;                       // no vertex of this tile has a successor: the rows stay -inf
+  if (MODE == 1 && (i0 + 1) / kCols + grp * kGroup > min(O - 1, i0 + kRows - 1 + T) / kCols) return;   // no block in this group
   const int F8 = F >> 3;
   unsigned char *qs = lk_smem;                                   // [2][F8][128][16 B]
   unsigned char *ks = qs + (size_t)2 * F8 * kRows * 16;          // [2][F8][64][16 B]
@@ -179,7 +208,9 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
   const int i = i0 + r;
   const bool rowlive = r < kRows && i < O - 1;   // has at least one successor (T >= 1)
   // destination blocks that hold a successor of some vertex of the tile: j in [i0 + 1, min(O - 1, i0 + 127 + T)]
-  const int jb_lo = (i0 + 1) / kCols, jb_hi = min(O - 1, i0 + kRows - 1 + T) / kCols;
+  const int jb_all_lo = (i0 + 1) / kCols, jb_all_hi = min(O - 1, i0 + kRows - 1 + T) / kCols;
+  const int jb_lo = MODE == 0 ? jb_all_lo : jb_all_lo + grp * kGroup;
+  const int jb_hi = MODE == 0 ? jb_all_hi : min(jb_all_hi, jb_lo + kGroup - 1);
   const float scale = rsqrtf((float)F) * kLog2e;  // scores in log2 units
   const uint32_t lanebase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
@@ -199,7 +230,7 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
   };
 
   // ---- pass 1: per head, the online maximum / sum of the row over its successors ---------------------------------
-  for (int c = 0; c < H; c++) {
+  for (int c = (MODE == 0 ? (int)blockIdx.y : H); c < (MODE == 0 ? (int)blockIdx.y + 1 : H); c++) {
     __syncthreads();                               // the previous head's MMAs are complete (everybody waited on `bar`)
     stage_operand(qs, qb, i0, kRows, L, H, F, c, scale);
     float m = neg_inf_f(), l = 0.f;
@@ -233,11 +264,17 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
     if (warp < 4) {
       // log2 of the head's normaliser minus the log2 gate: pass 2 subtracts it from the score
       const float lg = (rowlive) ? __ldg(log_gates + ((size_t)b * L + i) * H + c) * kLog2e : 0.f;
-      lse[c * kRows + r] = (rowlive && l > 0.f) ? m + log2f(l) - lg : __int_as_float(0x7f800000);   // +inf: contributes 0
+      if (i < L) stats[((size_t)b * H + c) * L + i] = (rowlive && l > 0.f) ? m + log2f(l) - lg : __int_as_float(0x7f800000);   // +inf: contributes 0
+    }
+  }
+  if (MODE == 1) {                                 // the statistics of my rows, all heads (written by the MODE 0 launch)
+    for (int x = threadIdx.x; x < H * kRows; x += kThreads) {
+      const int c = x / kRows, rr = x - c * kRows;
+      lse[x] = (i0 + rr < L) ? __ldg(stats + ((size_t)b * H + c) * L + i0 + rr) : __int_as_float(0x7f800000);
     }
   }
   // ---- pass 2: per destination block, the mixture over the heads ---------------------------------------------------
-  for (int jb = jb_lo; jb <= jb_hi; jb++) {
+  for (int jb = jb_lo; MODE == 1 && jb <= jb_hi; jb++) {
     float P[kCols];
 #pragma unroll
     for (int n = 0; n < kCols; n++) P[n] = 0.f;
@@ -282,11 +319,11 @@ using namespace dagb200;
 
 // q, key: [B][L][H][F] fp32 (the reshaped outputs of query_linear / key_linear), log_gates: [B][L][H] fp32
 // (log_softmax of gate_linear), output_length[b] = number of non-pad positions, links: [B][L][T] fp32, every element
-// written.  F a multiple of 16, 16 <= F <= 128; H <= 64.
+// written; stats: fp32 [B][H][L] scratch (per-head row normalisers).  F a multiple of 16, 16 <= F <= 128; H <= 64.
 extern "C" int dagb200_extract_links(const float *q, const float *key, const float *log_gates, const int64_t *output_length,
-                                     float *links, int B, int L, int H, int F, int T, void *stream) {
+                                     float *stats, float *links, int B, int L, int H, int F, int T, void *stream) {
   using namespace lk;
-  if (B < 0 || L < 1 || H < 1 || H > 64 || F < 16 || F > 128 || (F & 15) || T < 0) {
+  if (B < 0 || L < 1 || H < 1 || H > 64 || F < 16 || F > 128 || (F & 15) || T < 0 || B > 65535 || !stats) {
     set_error("extract_links: bad shape (F a multiple of 16 in [16, 128], 1 <= H <= 64)");
     return DAGB200_EINVAL;
   }
@@ -296,9 +333,15 @@ extern "C" int dagb200_extract_links(const float *q, const float *key, const flo
   fill_neg_inf_kernel<<<(int)std::min<size_t>((n + 1023) / 1024, (size_t)8 * sm_count()), 256, 0, st>>>(links, n);
   const int F8 = F >> 3;
   const size_t smem = (size_t)2 * F8 * (kRows + kCols) * 16 + (size_t)H * kRows * 4 + 64;
-  cudaFuncSetAttribute(extract_links_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((L + kRows - 1) / kRows, B);
-  extract_links_tcgen05_kernel<<<grid, kThreads, smem, st>>>(q, key, log_gates, output_length, links, L, H, F, T);
-  DAGB200_CHECK_LAUNCH("extract_links_tcgen05_kernel");
+  cudaFuncSetAttribute(extract_links_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(extract_links_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int rts = (L + kRows - 1) / kRows;
+  const int ngroups = ((L + kCols - 1) / kCols + kGroup - 1) / kGroup;
+  extract_links_tcgen05_kernel<0><<<dim3(rts, H, B), kThreads, smem, st>>>(q, key, log_gates, output_length, stats, links,
+                                                                          L, H, F, T, ngroups);
+  DAGB200_CHECK_LAUNCH("extract_links_tcgen05_kernel<0>");
+  extract_links_tcgen05_kernel<1><<<dim3(rts * ngroups, B), kThreads, smem, st>>>(q, key, log_gates, output_length, stats,
+                                                                                 links, L, H, F, T, ngroups);
+  DAGB200_CHECK_LAUNCH("extract_links_tcgen05_kernel<1>");
   return 0;
 }

@@ -116,9 +116,9 @@ int dagb200_dag_loss_backward(const void *grad_output, const void *alpha, const 
 
 /* Same contract as dagb200_dag_loss_backward, plus a device scratch of
  * dagb200_dag_loss_backward_workspace_bytes(B,M,L,T) bytes.  With it (fp32, not in exact mode) the backward runs as
- * two passes (dag_grad3.cu): one streaming pass that writes grad_match and bf16 hi/lo operand planes of exp(alpha),
- * exp(beta) with one integer frame per (row, 32-vertex block), and a tensor-core contraction over the target index
- * for grad_links.  With workspace == NULL it is exactly dagb200_dag_loss_backward.                        */
+ * three kernels (dag_grad4.cu): one streaming pass that writes grad_match and bf16 hi/lo operand planes of exp(alpha),
+ * exp(beta) with one integer frame per (row, 32-vertex block), the per-block-pair frame maxima, and a tcgen05
+ * contraction over the target index for grad_links.  With workspace == NULL it is exactly dagb200_dag_loss_backward. */
 size_t dagb200_dag_loss_backward_workspace_bytes(int B, int M, int L, int T);
 int dagb200_dag_loss_backward_ws(const void *grad_output, const void *alpha, const void *beta,
                                  const void *match, const void *links,
@@ -203,10 +203,11 @@ int dagb200_decode_viterbi_finish(const float *lattice, const float *links, cons
  * form (max_transition_length != -1):  links[b][i][k] = logsumexp_c( log_softmax_k( q[b,i,c,:].key[b,i+k+1,c,:] / sqrt(F) )
  * + log_gates[b,i,c] ), successors j = i+k+1 < output_length[b], -inf elsewhere.
  *   q, key: fp32 [B][L][H][F] (reshaped outputs of query_linear / key_linear); log_gates: fp32 [B][L][H];
- *   output_length: int64 [B] (non-pad positions); links: fp32 [B][L][T], every element written.
+ *   output_length: int64 [B] (non-pad positions); stats: fp32 [B][H][L] scratch; links: fp32 [B][L][T], every element
+ *   written.
  *   F a multiple of 16 in [16, 128], H <= 64.  tcgen05 (bf16 hi/lo split, fp32 accumulate); no [B,L,L,H] temporary. */
 int dagb200_extract_links(const float *q, const float *key, const float *log_gates, const int64_t *output_length,
-                          float *links, int B, int L, int H, int F, int T, void *stream);
+                          float *stats, float *links, int B, int L, int H, int F, int T, void *stream);
 
 /* ---- Data-parallel gradient exchange over NVLink peer memory (daspeech_b200/csrc/xchg.cu) ---------------------------
  * Replaces fairseq legacy_distributed_data_parallel.py:76-165 (one flat gradient buffer, divided by the world size,
