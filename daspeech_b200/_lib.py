@@ -50,7 +50,8 @@ SIGNATURES = {
     "dagb200_best_alignment_workspace_bytes": (_sz, [_int, _int, _int, _int]),
     "dagb200_dag_best_alignment": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int,
                                           _vp, _sz, _vp, _vp]),
-    "dagb200_extract_links": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),
+    "dagb200_extract_links_workspace_bytes": (_sz, [_int, _int, _int, _int]),
+    "dagb200_extract_links": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _sz, _vp]),
     "dagb200_peer_alloc": (_int, [_sz, ctypes.POINTER(ctypes.c_void_p)]),
     "dagb200_peer_free": (_int, [_vp]),
     "dagb200_peer_export": (_int, [_vp, _vp]),

@@ -6,17 +6,16 @@
 //   s[c][k]  = q[b,i,c,:] . key[b,j,c,:] / sqrt(F)                      einsum("bicf,bjcf->bijc") -> [B,L,L,H] fp32 (2.1 GB at C2)
 //   lp[c][k] = s[c][k] - logsumexp_k s[c][k]                             gather of the band, masked log_softmax over successors
 //   links[k] = logsumexp_c (lp[c][k] + log_gates[b,i,c])                 mixture over the heads
-// several [B,L,T,H] temporaries.  Here a CTA owns 128 consecutive vertices of one utterance and nothing is materialised
-// but the [B,L,T] result and [B,H,L] row normalisers (two launches: one CTA per (row tile, head), then one per (row
-// tile, pair of destination blocks)):
-//   pass 1  for every head: S = Q K^T tile by tile (128 x 64, K = F) on the tensor cores -- tcgen05.mma kind::f16 with
-//           both operands split bf16 hi/lo (3 MMAs per k16 step: 2^-16 relative, fp32 accumulate in TMEM) -- and the
-//           online maximum / sum of every row (thread = row = TMEM lane) -> lse[c] per row;
-//   pass 2  for every 64-column block, for every head: the same tile again, P[j] += exp(s - lse[c] + log_gate[c]);
-//           links = log P, written into the banded layout links[i][j-i-1].
-// The scores are recomputed instead of stored (12 MMAs of 128x64x16 per tile: the kernel is bound by the exponentials
-// and the operand staging, not by the tensor pipe).  Operands are converted from the fp32 projections while they are
-// staged into the canonical K-major core-matrix layout; one thread issues, completion through tcgen05.commit -> mbarrier.
+// several [B,L,T,H] temporaries.  Here nothing is materialised but the [B,L,T] result, [B,H,L] row normalisers and the
+// operands converted once (bf16 hi + lo, in the layout the MMAs read):
+//   links_convert_kernel          q, key -> operand stores (scale 1/sqrt(F) log2e folded into q)
+//   extract_links_tcgen05_kernel<0>  one CTA per (128-vertex row tile, head): S = Q K^T tile by tile (128 x 64, K = F) on the
+//           tensor cores -- tcgen05.mma kind::f16, both operands split bf16 hi/lo (3 MMAs per k16 step: 2^-16 relative,
+//           fp32 accumulate in TMEM) -- and the online maximum / sum of every row (thread = row = TMEM lane) -> lse[c];
+//   extract_links_tcgen05_kernel<1>  one CTA per (row tile, pair of 64-vertex destination blocks): the same tiles again for
+//           every head, P[j] += exp(s - lse[c] + log_gate[c]); links = log P, written into the band links[i][j-i-1].
+// The scores are recomputed instead of stored.  Tile operands arrive by cp.async while the previous tile is in its
+// epilogue; one thread issues the MMAs, completion through tcgen05.commit -> mbarrier.
 // Mixture weights below e^-87 of a row's total flush to 0, i.e. such a transition comes out as -inf where the reference
 // returns a finite value below -87 (the same contract as the blocked recurrences).
 #include <algorithm>
@@ -30,6 +29,7 @@ namespace lk {
 
 constexpr int kRows = 128;      // source vertices per CTA = M of the MMA = TMEM lanes
 constexpr int kCols = 64;       // destination vertices per tile = N of the MMA
+constexpr int kGroup = 2;       // destination blocks per CTA of the mixture launch
 constexpr int kThreads = 160;   // warps 0-3: rows (epilogue), warp 4: MMA issue; all five stage operands
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -104,46 +104,49 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// `nrows` vertices starting at `v0` of head c as an MMA operand: [plane hi|lo][k-core][row][8 bf16 along K], scaled.
-// Four items (32 bytes each) are requested per thread before the first one is converted: the staging of a tile is one
-// L2 latency, not one per item (the first version converted item by item and spent two thirds of a tile in here).
-__device__ __forceinline__ void stage_operand(unsigned char *dst, const float *__restrict__ src, int v0, int nrows, int L,
-                                              int H, int F, int c, float scale) {
-  constexpr int NB = 4;
+// Operand store: the projections converted ONCE into the layout the MMAs read -- per (utterance, head)
+// [plane bf16 hi | lo][k-core][Lp vertices][8 bf16 along K] (Lp = L rounded up to the row tile, zero rows beyond L), the
+// 1/sqrt(F) log2e scale folded into Q.  A tile operand is then 2 F/8 contiguous runs of nrows x 16 bytes, copied into
+// shared memory by cp.async (no registers, no conversion in the tile loop) while the previous tile is in its epilogue.
+__global__ void __launch_bounds__(256)
+links_convert_kernel(const float *__restrict__ src, unsigned char *__restrict__ dst, int L, int Lp, int H, int F, float scale,
+                     size_t nitems) {
   const int F8 = F >> 3;
-  const int nitems = nrows * F8;
-  const size_t plane = (size_t)F8 * nrows * 16;
-  for (int base = threadIdx.x; base < nitems; base += kThreads * NB) {
-    float4 a[NB], b[NB];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t item = (size_t)blockIdx.x * blockDim.x + threadIdx.x; item < nitems; item += stride) {
+    // item = ((b * H + c) * F8 + kc) * Lp + v : consecutive threads -> consecutive vertices (coalesced 16-byte stores)
+    const int v = (int)(item % Lp);
+    size_t rest = item / Lp;
+    const int kc = (int)(rest % F8); rest /= F8;
+    const int c = (int)(rest % H);
+    const size_t b = rest / H;
+    float x[8];
 #pragma unroll
-    for (int u = 0; u < NB; u++) {
-      const int item = base + u * kThreads;
-      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      b[u] = a[u];
-      if (item < nitems) {
-        const int kc = item / nrows, r = item - kc * nrows;   // consecutive threads: consecutive rows (conflict-free stores)
-        const int v = v0 + r;
-        if (v < L) {
-          const float4 *p = reinterpret_cast<const float4 *>(src + ((size_t)v * H + c) * F + 8 * kc);
-          a[u] = __ldg(p);
-          b[u] = __ldg(p + 1);
-        }
-      }
+    for (int e = 0; e < 8; e++) x[e] = 0.f;
+    if (v < L) {
+      const float4 *p = reinterpret_cast<const float4 *>(src + ((b * L + v) * H + c) * F + 8 * kc);
+      const float4 a = __ldg(p), bb = __ldg(p + 1);
+      x[0] = a.x * scale; x[1] = a.y * scale; x[2] = a.z * scale; x[3] = a.w * scale;
+      x[4] = bb.x * scale; x[5] = bb.y * scale; x[6] = bb.z * scale; x[7] = bb.w * scale;
     }
-#pragma unroll
-    for (int u = 0; u < NB; u++) {
-      const int item = base + u * kThreads;
-      if (item < nitems) {
-        const int kc = item / nrows, r = item - kc * nrows;
-        const float x[8] = {a[u].x * scale, a[u].y * scale, a[u].z * scale, a[u].w * scale,
-                            b[u].x * scale, b[u].y * scale, b[u].z * scale, b[u].w * scale};
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        unsigned char *q = dst + ((size_t)kc * nrows + r) * 16;
-        *reinterpret_cast<uint4 *>(q) = hi;
-        *reinterpret_cast<uint4 *>(q + plane) = lo;
-      }
-    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    unsigned char *o = dst + ((((b * H + c) * 2) * F8 + kc) * (size_t)Lp + v) * 16;
+    *reinterpret_cast<uint4 *>(o) = hi;
+    *reinterpret_cast<uint4 *>(o + (size_t)F8 * Lp * 16) = lo;
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// start the copy of `nrows` vertices from `v0` of one (utterance, head) operand store into an MMA operand buffer
+__device__ __forceinline__ void stage_async(unsigned char *dst, const unsigned char *__restrict__ conv, int v0, int nrows,
+                                            int Lp, int F8) {
+  const int nitems = 2 * F8 * nrows;
+  for (int item = threadIdx.x; item < nitems; item += kThreads) {
+    const int pk = item / nrows, r = item - pk * nrows;       // pk = plane * F8 + kc
+    cp_async16(dst + ((size_t)pk * nrows + r) * 16, conv + ((size_t)pk * Lp + v0 + r) * 16);
   }
 }
 
@@ -168,12 +171,11 @@ __device__ __forceinline__ void issue_tile(uint32_t tmem_d, uint32_t q_u32, uint
 // MODE 1 (grid: row tile x column group, utterance): pass 2 of kGroup destination blocks, all heads -> links.
 // Two launches instead of one CTA per row tile doing everything: the first row tile of an utterance has 16 destination
 // blocks x 8 heads x 2 passes = 256 tiles against 32 for the last one, and the kernel ran as long as its heaviest CTA.
-constexpr int kGroup = 2;
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restrict__ key, const float *__restrict__ log_gates,
-                             const int64_t *__restrict__ olen, float *__restrict__ stats, float *__restrict__ links, int L,
-                             int H, int F, int T, int ngroups) {
+__global__ void __launch_bounds__(kThreads, 3)
+extract_links_tcgen05_kernel(const unsigned char *__restrict__ qconv, const unsigned char *__restrict__ kconv,
+                             const float *__restrict__ log_gates, const int64_t *__restrict__ olen, float *__restrict__ stats,
+                             float *__restrict__ links, int L, int Lp, int H, int F, int T, int ngroups) {
   extern __shared__ __align__(128) unsigned char lk_smem[];
   const int b = MODE == 0 ? blockIdx.z : blockIdx.y;
   const int rt = MODE == 0 ? blockIdx.x : blockIdx.x / ngroups;
@@ -181,7 +183,11 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
   const int i0 = rt * kRows;
   const int O = min((int)olen[b], L);
   if (i0 >= O - 1) return;                       // no vertex of this tile has a successor: the rows stay -inf
-  if (MODE == 1 && (i0 + 1) / kCols + grp * kGroup > min(O - 1, i0 + kRows - 1 + T) / kCols) return;   // no block in this group
+  // destination blocks that hold a successor of some vertex of the tile: j in [i0 + 1, min(O - 1, i0 + 127 + T)]
+  const int jb_all_lo = (i0 + 1) / kCols, jb_all_hi = min(O - 1, i0 + kRows - 1 + T) / kCols;
+  const int jb_lo = MODE == 0 ? jb_all_lo : jb_all_lo + grp * kGroup;
+  const int jb_hi = MODE == 0 ? jb_all_hi : min(jb_all_hi, jb_lo + kGroup - 1);
+  if (jb_lo > jb_hi) return;                     // no block in this group
   const int F8 = F >> 3;
   unsigned char *qs = lk_smem;                                   // [2][F8][128][16 B]
   unsigned char *ks = qs + (size_t)2 * F8 * kRows * 16;          // [2][F8][64][16 B]
@@ -189,13 +195,32 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
   uint64_t *bar = reinterpret_cast<uint64_t *>(lse + (size_t)H * kRows);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float *qb = q + (size_t)b * L * H * F, *kb = key + (size_t)b * L * H * F;
+  const size_t head_bytes = (size_t)2 * F8 * Lp * 16;            // one (utterance, head) operand store
+  const unsigned char *qb = qconv + (size_t)b * H * head_bytes, *kb = kconv + (size_t)b * H * head_bytes;
+
+  // tiles of this CTA in order: MODE 0: (my head, jb_lo..jb_hi); MODE 1: for every block of the group, every head
+  const int ntiles = MODE == 0 ? jb_hi - jb_lo + 1 : (jb_hi - jb_lo + 1) * H;
+  auto tile_c = [&](int t) { return MODE == 0 ? (int)blockIdx.y : t % H; };
+  auto tile_jb = [&](int t) { return MODE == 0 ? jb_lo + t : jb_lo + t / H; };
+  auto stage_tile = [&](int t) {                 // asynchronous: returns at once
+    const int c = tile_c(t);
+    if (MODE == 1 || t == 0) stage_async(qs, qb + (size_t)c * head_bytes, i0, kRows, Lp, F8);
+    stage_async(ks, kb + (size_t)c * head_bytes, tile_jb(t) * kCols, kCols, Lp, F8);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_tile(0);
 
   if (threadIdx.x == 0) mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (MODE == 1) {                                 // the statistics of my rows, all heads (written by the MODE 0 launch)
+    for (int x = threadIdx.x; x < H * kRows; x += kThreads) {
+      const int c = x / kRows, rr = x - c * kRows;
+      lse[x] = (i0 + rr < L) ? __ldg(stats + ((size_t)b * H + c) * L + i0 + rr) : __int_as_float(0x7f800000);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -207,19 +232,19 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
   const int r = threadIdx.x;                     // row of the tile (threads 0..127)
   const int i = i0 + r;
   const bool rowlive = r < kRows && i < O - 1;   // has at least one successor (T >= 1)
-  // destination blocks that hold a successor of some vertex of the tile: j in [i0 + 1, min(O - 1, i0 + 127 + T)]
-  const int jb_all_lo = (i0 + 1) / kCols, jb_all_hi = min(O - 1, i0 + kRows - 1 + T) / kCols;
-  const int jb_lo = MODE == 0 ? jb_all_lo : jb_all_lo + grp * kGroup;
-  const int jb_hi = MODE == 0 ? jb_all_hi : min(jb_all_hi, jb_lo + kGroup - 1);
-  const float scale = rsqrtf((float)F) * kLog2e;  // scores in log2 units
   const uint32_t lanebase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
-  // one tile: stage K, run the MMAs, wait; on return the accumulator of (head c, block jb) sits in TMEM
-  auto run_tile = [&](int c, int jb) {
-    stage_operand(ks, kb, jb * kCols, kCols, L, H, F, c, 1.f);
+  float m = neg_inf_f(), l = 0.f;                // MODE 0: online maximum / sum of my row over its successors
+  float P[MODE == 1 ? kCols : 1];                // MODE 1: mixture weights of the current destination block
+#pragma unroll
+  for (int n = 0; n < (MODE == 1 ? kCols : 1); n++) P[n] = 0.f;
+
+  for (int t = 0; t < ntiles; t++) {
+    const int c = tile_c(t), jb = tile_jb(t);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     proxy_fence_async_smem();
     tc_fence_before();
-    __syncthreads();                               // operands staged; every row is done with the previous accumulator
+    __syncthreads();                               // operands landed; every row is done with the previous accumulator
     if (warp == 4 && lane == 0) {
       tc_fence_after();
       issue_tile(tmem, q_u32, k_u32, F, bar);
@@ -227,16 +252,9 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-  };
-
-  // ---- pass 1: per head, the online maximum / sum of the row over its successors ---------------------------------
-  for (int c = (MODE == 0 ? (int)blockIdx.y : H); c < (MODE == 0 ? (int)blockIdx.y + 1 : H); c++) {
-    __syncthreads();                               // the previous head's MMAs are complete (everybody waited on `bar`)
-    stage_operand(qs, qb, i0, kRows, L, H, F, c, scale);
-    float m = neg_inf_f(), l = 0.f;
-    for (int jb = jb_lo; jb <= jb_hi; jb++) {
-      run_tile(c, jb);
-      if (warp < 4) {
+    if (t + 1 < ntiles) stage_tile(t + 1);         // the MMAs have read the buffers: refill them under the epilogue
+    if (warp < 4) {
+      if (MODE == 0) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           float v[32];
@@ -252,37 +270,14 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
           }
           if (tm > neg_inf_f()) {
             const float mn = fmaxf(m, tm);
-            float s = 0.f;
+            float sum = 0.f;
 #pragma unroll
-            for (int n = 0; n < 32; n++) s += ex2(v[n] - mn);     // ex2(-inf) = 0
-            l = l * ex2(m - mn) + s;
+            for (int n = 0; n < 32; n++) sum += ex2(v[n] - mn);     // ex2(-inf) = 0
+            l = l * ex2(m - mn) + sum;
             m = mn;
           }
         }
-      }
-    }
-    if (warp < 4) {
-      // log2 of the head's normaliser minus the log2 gate: pass 2 subtracts it from the score
-      const float lg = (rowlive) ? __ldg(log_gates + ((size_t)b * L + i) * H + c) * kLog2e : 0.f;
-      if (i < L) stats[((size_t)b * H + c) * L + i] = (rowlive && l > 0.f) ? m + log2f(l) - lg : __int_as_float(0x7f800000);   // +inf: contributes 0
-    }
-  }
-  if (MODE == 1) {                                 // the statistics of my rows, all heads (written by the MODE 0 launch)
-    for (int x = threadIdx.x; x < H * kRows; x += kThreads) {
-      const int c = x / kRows, rr = x - c * kRows;
-      lse[x] = (i0 + rr < L) ? __ldg(stats + ((size_t)b * H + c) * L + i0 + rr) : __int_as_float(0x7f800000);
-    }
-  }
-  // ---- pass 2: per destination block, the mixture over the heads ---------------------------------------------------
-  for (int jb = jb_lo; MODE == 1 && jb <= jb_hi; jb++) {
-    float P[kCols];
-#pragma unroll
-    for (int n = 0; n < kCols; n++) P[n] = 0.f;
-    for (int c = 0; c < H; c++) {
-      __syncthreads();
-      stage_operand(qs, qb, i0, kRows, L, H, F, c, scale);
-      run_tile(c, jb);
-      if (warp < 4) {
+      } else {
         const float z = lse[c * kRows + r];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -291,16 +286,26 @@ extract_links_tcgen05_kernel(const float *__restrict__ q, const float *__restric
 #pragma unroll
           for (int n = 0; n < 32; n++) P[32 * h + n] += ex2(v[n] - z);   // z = +inf for a dead row / head: adds 0
         }
-      }
-    }
-    if (warp < 4 && rowlive) {
-      float *row = links + ((size_t)b * L + i) * T;
+        if (c == H - 1) {                          // the block is complete: ln of the mixture into the band
+          if (rowlive) {
+            float *row = links + ((size_t)b * L + i) * T;
 #pragma unroll
-      for (int n = 0; n < kCols; n++) {
-        const int j = jb * kCols + n;
-        if (j > i && j < O && j - i - 1 < T) row[j - i - 1] = P[n] > 0.f ? log2f(P[n]) * kLn2 : neg_inf_f();
+            for (int n = 0; n < kCols; n++) {
+              const int j = jb * kCols + n;
+              if (j > i && j < O && j - i - 1 < T) row[j - i - 1] = P[n] > 0.f ? log2f(P[n]) * kLn2 : neg_inf_f();
+            }
+          }
+#pragma unroll
+          for (int n = 0; n < kCols; n++) P[n] = 0.f;
+        }
       }
     }
+  }
+  if (MODE == 0 && warp < 4 && i < L) {
+    // log2 of the head's normaliser minus the log2 gate: the mixture pass subtracts it from the score
+    const int c = blockIdx.y;
+    const float lg = rowlive ? __ldg(log_gates + ((size_t)b * L + i) * H + c) * kLog2e : 0.f;
+    stats[((size_t)b * H + c) * L + i] = (rowlive && l > 0.f) ? m + log2f(l) - lg : __int_as_float(0x7f800000);   // +inf: adds 0
   }
   tc_fence_before();
   __syncthreads();
@@ -319,29 +324,54 @@ using namespace dagb200;
 
 // q, key: [B][L][H][F] fp32 (the reshaped outputs of query_linear / key_linear), log_gates: [B][L][H] fp32
 // (log_softmax of gate_linear), output_length[b] = number of non-pad positions, links: [B][L][T] fp32, every element
-// written; stats: fp32 [B][H][L] scratch (per-head row normalisers).  F a multiple of 16, 16 <= F <= 128; H <= 64.
+// written; workspace: dagb200_extract_links_workspace_bytes(B, L, H, F) bytes of device scratch (the converted operand
+// stores and the per-head row normalisers).  F a multiple of 16, 16 <= F <= 128; H <= 64.
+extern "C" size_t dagb200_extract_links_workspace_bytes(int B, int L, int H, int F) {
+  if (B <= 0 || L <= 0 || H <= 0 || F <= 0) return 0;
+  const size_t Lp = (size_t)(L + lk::kRows - 1) / lk::kRows * lk::kRows;
+  const size_t conv = (size_t)B * H * Lp * F * 4;              // hi + lo planes of bf16 = 4 bytes per element
+  const size_t stats = ((size_t)B * H * L * 4 + 255) / 256 * 256;
+  return 2 * conv + stats;
+}
+
 extern "C" int dagb200_extract_links(const float *q, const float *key, const float *log_gates, const int64_t *output_length,
-                                     float *stats, float *links, int B, int L, int H, int F, int T, void *stream) {
+                                     float *links, int B, int L, int H, int F, int T, void *workspace, size_t workspace_bytes,
+                                     void *stream) {
   using namespace lk;
-  if (B < 0 || L < 1 || H < 1 || H > 64 || F < 16 || F > 128 || (F & 15) || T < 0 || B > 65535 || !stats) {
+  if (B < 0 || L < 1 || H < 1 || H > 64 || F < 16 || F > 128 || (F & 15) || T < 0 || B > 65535) {
     set_error("extract_links: bad shape (F a multiple of 16 in [16, 128], 1 <= H <= 64)");
     return DAGB200_EINVAL;
   }
   if (B == 0 || T == 0) return 0;
+  if (!workspace || workspace_bytes < dagb200_extract_links_workspace_bytes(B, L, H, F)) {
+    set_error("extract_links: workspace of %zu bytes required", dagb200_extract_links_workspace_bytes(B, L, H, F));
+    return DAGB200_EINVAL;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)B * L * T;
   fill_neg_inf_kernel<<<(int)std::min<size_t>((n + 1023) / 1024, (size_t)8 * sm_count()), 256, 0, st>>>(links, n);
   const int F8 = F >> 3;
+  const int Lp = (L + kRows - 1) / kRows * kRows;
+  const size_t conv = (size_t)B * H * Lp * F * 4;
+  unsigned char *qconv = (unsigned char *)workspace, *kconv = qconv + conv;
+  float *stats = reinterpret_cast<float *>(kconv + conv);
+  {
+    const size_t nitems = (size_t)B * H * F8 * Lp;
+    const int grid = (int)std::min<size_t>((nitems + 255) / 256, (size_t)16 * sm_count());
+    links_convert_kernel<<<grid, 256, 0, st>>>(q, qconv, L, Lp, H, F, (1.f / sqrtf((float)F)) * lk::kLog2e, nitems);
+    links_convert_kernel<<<grid, 256, 0, st>>>(key, kconv, L, Lp, H, F, 1.f, nitems);
+    DAGB200_CHECK_LAUNCH("links_convert_kernel");
+  }
   const size_t smem = (size_t)2 * F8 * (kRows + kCols) * 16 + (size_t)H * kRows * 4 + 64;
   cudaFuncSetAttribute(extract_links_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(extract_links_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int rts = (L + kRows - 1) / kRows;
+  const int rts = Lp / kRows;
   const int ngroups = ((L + kCols - 1) / kCols + kGroup - 1) / kGroup;
-  extract_links_tcgen05_kernel<0><<<dim3(rts, H, B), kThreads, smem, st>>>(q, key, log_gates, output_length, stats, links,
-                                                                          L, H, F, T, ngroups);
+  extract_links_tcgen05_kernel<0><<<dim3(rts, H, B), kThreads, smem, st>>>(qconv, kconv, log_gates, output_length, stats,
+                                                                          links, L, Lp, H, F, T, ngroups);
   DAGB200_CHECK_LAUNCH("extract_links_tcgen05_kernel<0>");
-  extract_links_tcgen05_kernel<1><<<dim3(rts * ngroups, B), kThreads, smem, st>>>(q, key, log_gates, output_length, stats,
-                                                                                 links, L, H, F, T, ngroups);
+  extract_links_tcgen05_kernel<1><<<dim3(rts * ngroups, B), kThreads, smem, st>>>(qconv, kconv, log_gates, output_length,
+                                                                                 stats, links, L, Lp, H, F, T, ngroups);
   DAGB200_CHECK_LAUNCH("extract_links_tcgen05_kernel<1>");
   return 0;
 }

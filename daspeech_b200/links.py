@@ -78,9 +78,11 @@ class _ExtractLinksFunc(torch.autograd.Function):
         g = log_gates.detach().float().contiguous()
         ol = output_length.contiguous()
         links = torch.empty((B, L, translen), dtype=torch.float32, device=q.device)
-        stats = torch.empty((B, H, L), dtype=torch.float32, device=q.device)      # per-head row normalisers (scratch)
+        nbytes = int(lib.dagb200_extract_links_workspace_bytes(B, L, H, Fd))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)              # converted operands + row normalisers
         with torch.cuda.device(q.device):
-            rc = lib.dagb200_extract_links(_ptr(q), _ptr(k), _ptr(g), _ptr(ol), _ptr(stats), _ptr(links), B, L, H, Fd, translen,
+            rc = lib.dagb200_extract_links(_ptr(q), _ptr(k), _ptr(g), _ptr(ol), _ptr(links), B, L, H, Fd, translen,
+                                           _ptr(ws), nbytes,
                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "extract_links")
         ctx.save_for_backward(query_chunks, key_chunks, log_gates, ol)

@@ -203,11 +203,14 @@ int dagb200_decode_viterbi_finish(const float *lattice, const float *links, cons
  * form (max_transition_length != -1):  links[b][i][k] = logsumexp_c( log_softmax_k( q[b,i,c,:].key[b,i+k+1,c,:] / sqrt(F) )
  * + log_gates[b,i,c] ), successors j = i+k+1 < output_length[b], -inf elsewhere.
  *   q, key: fp32 [B][L][H][F] (reshaped outputs of query_linear / key_linear); log_gates: fp32 [B][L][H];
- *   output_length: int64 [B] (non-pad positions); stats: fp32 [B][H][L] scratch; links: fp32 [B][L][T], every element
- *   written.
+ *   output_length: int64 [B] (non-pad positions); links: fp32 [B][L][T], every element written; workspace:
+ *   dagb200_extract_links_workspace_bytes(B,L,H,F) bytes of device scratch (operands converted once into the MMA
+ *   layout, per-head row normalisers).
  *   F a multiple of 16 in [16, 128], H <= 64.  tcgen05 (bf16 hi/lo split, fp32 accumulate); no [B,L,L,H] temporary. */
+size_t dagb200_extract_links_workspace_bytes(int B, int L, int H, int F);
 int dagb200_extract_links(const float *q, const float *key, const float *log_gates, const int64_t *output_length,
-                          float *stats, float *links, int B, int L, int H, int F, int T, void *stream);
+                          float *links, int B, int L, int H, int F, int T, void *workspace, size_t workspace_bytes,
+                          void *stream);
 
 /* ---- Data-parallel gradient exchange over NVLink peer memory (daspeech_b200/csrc/xchg.cu) ---------------------------
  * Replaces fairseq legacy_distributed_data_parallel.py:76-165 (one flat gradient buffer, divided by the world size,
