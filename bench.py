@@ -696,6 +696,25 @@ def main():
         parts["glat_force_emit"] = {"ms": ms_g, "algorithmic_bytes": by_g, "gbs": by_g / ms_g / 1e6,
                                     "frac": by_g / ms_g / 1e6 / peak_gbs, "torch_ops_ms": ms_gt}
         del mm, keepm, prevm
+        # next row: the transition log-probabilities from the link heads (H = 8 heads of 64 features,
+        # the models' decoder width), fused tcgen05 forward vs the model's op sequence run by torch on 8 utterances
+        try:
+            from daspeech_b200 import links as dlinks
+            Hh, Fh = 8, 64
+            gq = torch.Generator(device=dev).manual_seed(7)
+            qh = torch.randn(B, L, Hh, Fh, device=dev, generator=gq)
+            kh = torch.randn(B, L, Hh, Fh, device=dev, generator=gq)
+            lgh = torch.log_softmax(torch.randn(B, L, Hh, device=dev, generator=gq), -1)
+            with torch.no_grad():
+                ms_l = timeit(lambda: dlinks.extract_links_from_chunks(qh, kh, lgh, olen, T, fused=True))
+                nb = min(B, 8)
+                ms_lt = timeit(lambda: dlinks.torch_extract_links(qh[:nb], kh[:nb], lgh[:nb], olen[:nb], T), 3)
+            parts["extract_links"] = {"shape": {"B": B, "L": L, "H": Hh, "F": Fh, "T": T}, "ms": ms_l,
+                                      "torch_op_sequence_ms": ms_lt * B / nb,
+                                      "note": "op sequence timed on %d utterances ([B,L,L,H] product: 2.1 GB per 8) and scaled" % nb}
+            del qh, kh, lgh
+        except Exception as e:   # noqa: BLE001 -- informational part
+            parts["extract_links"] = {"error": repr(e)[:200]}
 
         # the banded secondary configuration (T = 32, the reference tuner's setting) and the tuner's shape family
         def fwd_bwd(B_, L_, M_, T_, n=10):
