@@ -286,13 +286,20 @@ class NvlsGradExchange:
         return self.buffer
 
 
+def exchange_order(kind: str, world_size: int):
+    """Mechanisms to try, in order.  Two ranks: the copy engines move the 150 MB slices without holding SMs (0.69 ms) and
+    the in-switch form has nothing to save (it moves MORE bytes than point-to-point at N = 2); from four ranks on the
+    switch reduces (300 MB per GPU and direction whatever N, against 2 * (N-1)/N * 300 MB point-to-point)."""
+    if kind != "auto":
+        return (kind,)
+    return ("peer", "nvls", "nccl") if world_size <= 2 else ("nvls", "peer", "nccl")
+
+
 def make_grad_exchange(numel: int, device, kind: str = "auto"):
     """The gradient exchange for this box: "nvls" (in-switch), "peer" (copy engines), "nccl", or "auto" = the first of
     those that can be set up.  Returns (exchange, kind)."""
     _, ws = world()
-    # two ranks: the copy engines move the 150 MB slices without holding SMs (0.69 ms) and the in-switch form has
-    # nothing to save (it moves more bytes than point-to-point at N = 2); from four ranks on the switch reduces
-    order = {"auto": ("peer", "nvls", "nccl") if ws <= 2 else ("nvls", "peer", "nccl")}.get(kind, (kind,))
+    order = exchange_order(kind, ws)
     last = None
     for k in order:
         try:

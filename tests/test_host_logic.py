@@ -93,3 +93,34 @@ def test_prefetcher_has_no_cpu_path_and_numa_binding_is_best_effort():
         with pytest.raises(RuntimeError, match="needs a CUDA device"):
             prefetch.DevicePrefetcher(iter([(torch.zeros(2),)]), torch.device("cpu"))
     assert prefetch.bind_host_to_gpu(0) in (True, False)
+
+
+def test_gradient_exchange_order_by_world_size():
+    from daspeech_b200.dist import exchange_order
+    assert exchange_order("auto", 2) == ("peer", "nvls", "nccl")
+    assert exchange_order("auto", 4)[0] == "nvls" and exchange_order("auto", 8)[-1] == "nccl"
+    assert exchange_order("nccl", 8) == ("nccl",)
+
+
+def test_link_rows_helper_equals_the_full_op_sequence_with_gradients():
+    """daspeech_b200.links._torch_rows (the chunked recomputation behind the fused op's backward) against the full
+    mirror of the reference op sequence: same values, same -inf pattern, same gradients, no NaN from dead rows."""
+    import torch
+    from daspeech_b200 import links as dl
+    torch.manual_seed(0)
+    B, L, H, Fd, T = 2, 90, 3, 16, 40
+    q = torch.randn(B, L, H, Fd, requires_grad=True)
+    k = torch.randn(B, L, H, Fd, requires_grad=True)
+    g = torch.log_softmax(torch.randn(B, L, H), -1).requires_grad_()
+    ol = torch.tensor([90, 37])
+    full = dl.torch_extract_links(q, k, g, ol, T)
+    rows = torch.cat([dl._torch_rows(q, k, g, ol, T, i0, min(L, i0 + 32)) for i0 in range(0, L, 32)], 1)
+    fin = torch.isfinite(full)
+    assert torch.equal(fin, torch.isfinite(rows))
+    assert float((full - rows)[fin].abs().max()) <= 1e-6
+    w = torch.randn_like(full)
+    g1 = torch.autograd.grad((full.masked_fill(~fin, 0) * w).sum(), [q, k, g])
+    g2 = torch.autograd.grad((rows.masked_fill(~fin, 0) * w).sum(), [q, k, g])
+    for a, b in zip(g1, g2):
+        assert torch.isfinite(b).all()
+        assert float((a - b).abs().max()) <= 1e-5
